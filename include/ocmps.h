@@ -1,0 +1,116 @@
+/* ocmps.h -- C ABI of libocmps: the B200-native Bose-Hubbard tDMRG / optimal-control engine.
+ *
+ * The reference (fskovbo/OptimalControlMPS) has no FFI: its hot path is the C++ classes
+ * BH_tDMRG (include/BH_tDMRG.hpp:16-40) and OptimalControl<TimeStepper>
+ * (include/OptimalControl.hpp:17-76) calling ITensor on the CPU.  This header is the boundary a
+ * maintainer binds instead of ITensor: every entry point below names the reference call it
+ * replaces.  Plain C types only; opaque handles; caller-owned host buffers; library-owned device
+ * memory; every function returns 0 on success and a negative code on failure, with the message
+ * available from ocmps_last_error().  There is no CPU fallback: without a CUDA device
+ * ocmps_ctx_create fails.
+ *
+ * Conventions
+ *   L      chain length, sites are 0-based in this API (the reference is 1-based)
+ *   D      local dimension = reference "d"+1 (include/BH_sites.h:73-91)
+ *   MPS    site tensor j is a row-major complex128 array A[l][s][r] (chi_j x D x chi_{j+1});
+ *          `tensors` is the concatenation over sites; `bond_dims` has L+1 entries;
+ *          `charges` is the concatenation over the L+1 bonds of the boson number to the left of
+ *          each bond index (the QN labels of ITensor's IQIndex, include/BH_sites.h:78-88).
+ *   complex numbers cross the ABI as interleaved (re, im) doubles.
+ */
+#ifndef OCMPS_H
+#define OCMPS_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ocmps_ctx ocmps_ctx;           /* one per GPU */
+typedef struct ocmps_mps ocmps_mps;           /* device-resident MPS (replaces itensor::IQMPS) */
+typedef struct ocmps_stepper ocmps_stepper;   /* replaces class BH_tDMRG */
+typedef struct ocmps_store ocmps_store;       /* Nt time slices resident in HBM (replaces std::vector<IQMPS> psi_t / xi_t / xiHlist,
+                                                 include/OptimalControl.hpp:26-28) */
+
+#define OCMPS_OK 0
+#define OCMPS_ERR_INVALID (-1)
+#define OCMPS_ERR_CUDA (-2)
+#define OCMPS_ERR_CAPACITY (-3)
+#define OCMPS_ERR_NUMERIC (-4)
+
+const char* ocmps_last_error(void);
+int ocmps_version(void);
+/* number of CUDA kernels launched by this library so far (bench.py reports it as gpu_launches) */
+long long ocmps_launch_count(void);
+
+/* ---- context ---- */
+int ocmps_ctx_create(int device, ocmps_ctx** out);
+int ocmps_ctx_destroy(ocmps_ctx* ctx);
+int ocmps_ctx_synchronize(ocmps_ctx* ctx);
+
+/* ---- MPS container (itensor::IQMPS in the reference's signatures) ---- */
+int ocmps_mps_create(ocmps_ctx* ctx, int L, int D, int chi_cap, ocmps_mps** out);
+int ocmps_mps_destroy(ocmps_mps* mps);
+int ocmps_mps_upload(ocmps_mps* mps, const int* bond_dims, const int* charges, const double* tensors, int llim, int rlim);
+/* sizes needed by download: number of complex elements and number of charge labels */
+int ocmps_mps_sizes(ocmps_mps* mps, long long* n_elems, long long* n_charges);
+int ocmps_mps_download(ocmps_mps* mps, int* bond_dims, int* charges, double* tensors, int* llim, int* rlim);
+int ocmps_mps_bond_dims(ocmps_mps* mps, int* bond_dims);       /* linkInd(psi,b).m(), main/AnalyzeBondDim.cpp:140 */
+int ocmps_mps_copy(ocmps_mps* dst, ocmps_mps* src);            /* IQMPS copy, e.g. src/OptimalControl.cpp:379-380 */
+int ocmps_mps_norm(ocmps_mps* mps, double* out);               /* itensor::norm(psi), src/OptimalControl.cpp:257 */
+/* overlapC(a,b) = <a|b> (first argument conjugated), src/OptimalControl.cpp:242,261,272,450 */
+int ocmps_overlap(ocmps_mps* a, ocmps_mps* b, double* re_im);
+/* overlapC(a, propDeriv, b) = <a|K|b>, K = sum_j 1/2 n_j(n_j-1), src/OptimalControl.cpp:220,227,417 */
+int ocmps_overlap_K(ocmps_mps* a, ocmps_mps* b, double* re_im);
+
+/* ---- time stepper (class BH_tDMRG) ----
+ * cutoff < 0 / maxm <= 0 mean "key not given" (ITensor defaults 1e-16 / 5000, tests/CostTests.cpp:41).
+ * chi_cap is the allocated bond capacity; a truncation that keeps more raises OCMPS_ERR_CAPACITY.
+ * rel_cutoff selects ITensor's DoRelCutoff for the Cutoff rule. */
+int ocmps_stepper_create(ocmps_ctx* ctx, int L, int D, double J, double tstep, double cutoff, int maxm, int chi_cap,
+                         int rel_cutoff, ocmps_stepper** out);                 /* BH_tDMRG::BH_tDMRG, src/BH_tDMRG.cpp:3-15 */
+int ocmps_stepper_destroy(ocmps_stepper* st);
+int ocmps_stepper_set_tstep(ocmps_stepper* st, double tstep);                    /* BH_tDMRG::setTstep :61-65 */
+double ocmps_stepper_get_tstep(ocmps_stepper* st);                                /* BH_tDMRG::getTstep :68-71 */
+/* BH_tDMRG::step(psi, from, to, propagateForward), src/BH_tDMRG.cpp:111-125 (in place) */
+int ocmps_step(ocmps_stepper* st, ocmps_mps* psi, double from, double to, int forward);
+/* exactApplyMPO(stepper.propagatorDeriv(u), psi, stepper.getArgs()), src/OptimalControl.cpp:256,302,362 */
+int ocmps_apply_K(ocmps_stepper* st, ocmps_mps* in, ocmps_mps* out);
+/* the op list one step executes (for tests): writes up to `cap` quadruples (kind, a, b, c); returns the count */
+int ocmps_stepper_schedule(ocmps_stepper* st, int* quads, int cap);
+/* the two-site J gate exp(-+ i tstep h) as D^2 x D^2 interleaved complex (BondGate, src/BH_tDMRG.cpp:35-36) */
+int ocmps_stepper_gate(ocmps_stepper* st, int forward, double* out);
+
+/* ---- resident slice stores and sweeps (OptimalControl::calcPsi / calcXi / calcDivT) ---- */
+int ocmps_store_create(ocmps_ctx* ctx, int L, int D, int chi_cap, int nslots, ocmps_store** out);
+int ocmps_store_destroy(ocmps_store* store);
+int ocmps_store_get(ocmps_store* store, int slot, ocmps_mps* out);            /* psi_t[slot] -> mps */
+int ocmps_store_put(ocmps_store* store, int slot, ocmps_mps* in);
+int ocmps_store_bond_dims(ocmps_store* store, int* out /* nslots*(L+1) */);
+/* calcPsi (src/OptimalControl.cpp:376-390): store[0]=psi_init, store[i+1]=step(store[i],u[i],u[i+1],fwd) */
+int ocmps_forward_sweep(ocmps_stepper* st, ocmps_mps* psi_init, const double* u, int Nt, ocmps_store* psi_store);
+/* calcXi (:393-407): store[Nt-1]=psi_target, store[i-1]=step(store[i],u[i],u[i-1],bwd) */
+int ocmps_backward_sweep(ocmps_stepper* st, ocmps_mps* psi_target, const double* u, int Nt, ocmps_store* xi_store);
+/* both sweeps enqueued on two streams (the reference's two std::threads, :424-430) */
+int ocmps_sweep_pair(ocmps_stepper* st, ocmps_mps* psi_init, ocmps_mps* psi_target, const double* u, int Nt,
+                     ocmps_store* psi_store, ocmps_store* xi_store);
+/* BFGS branch (:217-229): xi is propagated backwards without being stored, divT filled on the fly */
+int ocmps_backward_sweep_divT(ocmps_stepper* st, ocmps_mps* psi_target, const double* u, int Nt, ocmps_store* psi_store,
+                              double* divT /* 2*Nt */);
+/* out[i] = <bra|store[i]> for all slots (calcFidelityForAllT :471-491, calcCost :450) */
+int ocmps_store_overlaps(ocmps_store* store, ocmps_mps* bra, int Nt, double* out /* 2*Nt */);
+/* divT[i] = <xi_i|K|psi_i> (calcDivT :410-419) */
+int ocmps_store_divT(ocmps_store* xi_store, ocmps_store* psi_store, int Nt, double* out /* 2*Nt */);
+/* xiHlist[i] = exactApplyMPO(K, xi_t[i], args) for all i (:300-303) */
+int ocmps_store_apply_K(ocmps_stepper* st, ocmps_store* in, int Nt, ocmps_store* out);
+/* calcHessianRow (:252-279) for `nrows` rows listed in `rows`: for every row r the raw ingredients are returned,
+ *   ovl[r*Nt + j] = <xiH_j | psiH_r(t_j)>  (j = r .. Nt-2), norm[r] = ||K psi_r||;
+ * the caller assembles H (it also needs divT and the regularisation).  `nchains` independent rows are in flight at once. */
+int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* xiH_store, const double* u, int Nt,
+                       const int* rows, int nrows, int nchains, double* ovl /* 2*Nt*Nt */, double* norms /* Nt */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCMPS_H */

@@ -1,0 +1,258 @@
+// Bandwidth-type kernels of the engine: Trotter gate application on the merged two-site tensor,
+// diagonal on-site phases, slice-store copies, transfer-matrix planning / fix-ups, K|psi> expansion.
+#include "ocmps_internal.h"
+
+namespace {
+
+int grid_for(long long elems, int threads, int cap = 1184) {
+  long long g = (elems + threads - 1) / threads;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+__global__ void merge_setup_kernel(GemmDesc* d, const cplx* A1, const cplx* A2, cplx* theta, const int* dimL, const int* dimM,
+                                   const int* dimR, int D) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  GemmDesc g;
+  g.A = A1; g.B = A2; g.C = theta;
+  g.M = (*dimL) * D; g.K = *dimM; g.N = D * (*dimR);
+  g.lda = g.K; g.ldb = g.N; g.ldc = g.N;
+  g.opA = g.opB = 0; g.pad = 0;
+  *d = g;
+}
+
+// theta'[l,t1,t2,r] = o1[t1] o2[t2] sum_{s1,s2} G[(t1,t2),(s1,s2)] i1[s1] i2[s2] theta[l,s1,s2,r]
+// (src/BH_tDMRG.cpp:150-159).  One thread per (l, r); the D^2 x D^2 gate sits in shared memory.
+template <int D>
+__global__ void __launch_bounds__(128) gate_apply_kernel(cplx* __restrict__ theta, const int* dimL, const int* dimR,
+                                                        const cplx* __restrict__ G, Phases ph) {
+  extern __shared__ __align__(16) unsigned char gate_smem[];
+  cplx* W = reinterpret_cast<cplx*>(gate_smem);
+  const int chiL = *dimL, chiR = *dimR;
+  for (int e = threadIdx.x; e < D * D * D * D; e += blockDim.x) {
+    const int row = e / (D * D), col = e % (D * D);
+    const int t1 = row / D, t2 = row % D, s1 = col / D, s2 = col % D;
+    // combined scalar factor pin[s1] pin[s2] pout[t1] pout[t2]
+    double fr = ph.re[0][s1], fi = ph.im[0][s1];
+    double xr = fr * ph.re[1][s2] - fi * ph.im[1][s2], xi = fr * ph.im[1][s2] + fi * ph.re[1][s2];
+    fr = xr * ph.re[2][t1] - xi * ph.im[2][t1]; fi = xr * ph.im[2][t1] + xi * ph.re[2][t1];
+    xr = fr * ph.re[3][t2] - fi * ph.im[3][t2]; xi = fr * ph.im[3][t2] + fi * ph.re[3][t2];
+    const cplx g = G[e];
+    W[e] = make_double2(g.x * xr - g.y * xi, g.x * xi + g.y * xr);
+  }
+  __syncthreads();
+  const long long total = (long long)chiL * chiR;
+  const long long rowstride = (long long)D * chiR;          // stride of s1 (elements)
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int l = (int)(e / chiR), r = (int)(e % chiR);
+    cplx* base = theta + (long long)l * D * rowstride + r;
+    cplx in[D * D];
+#pragma unroll
+    for (int s1 = 0; s1 < D; ++s1)
+#pragma unroll
+      for (int s2 = 0; s2 < D; ++s2) in[s1 * D + s2] = base[s1 * rowstride + (long long)s2 * chiR];
+#pragma unroll 1
+    for (int row = 0; row < D * D; ++row) {
+      double ar = 0.0, ai = 0.0;
+#pragma unroll
+      for (int col = 0; col < D * D; ++col) {
+        const cplx w = W[row * D * D + col];
+        ar += w.x * in[col].x - w.y * in[col].y;
+        ai += w.x * in[col].y + w.y * in[col].x;
+      }
+      base[(row / D) * rowstride + (long long)(row % D) * chiR] = make_double2(ar, ai);
+    }
+  }
+}
+
+__global__ void site_phase_kernel(cplx* A, const int* dimL, const int* dimR, int D, Phases ph, int which) {
+  const int chiL = *dimL, chiR = *dimR;
+  const long long total = (long long)chiL * D * chiR;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)((e / chiR) % D);
+    const cplx u = A[e];
+    const double pr = ph.re[which][s], pi = ph.im[which][s];
+    A[e] = make_double2(u.x * pr - u.y * pi, u.x * pi + u.y * pr);
+  }
+}
+
+__global__ void pack_copy_kernel(SitePtrs src, cplx* dst_base, SiteOffs offs, const int* dims, int D) {
+  const int j = blockIdx.y;
+  const long long count = (long long)dims[j] * D * dims[j + 1];
+  const cplx* s = src.p[j];
+  cplx* d = dst_base + offs.o[j];
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x) d[e] = s[e];
+}
+__global__ void unpack_copy_kernel(const cplx* src_base, SitePtrs dst, SiteOffs offs, const int* dims, int D) {
+  const int j = blockIdx.y;
+  const long long count = (long long)dims[j] * D * dims[j + 1];
+  const cplx* s = src_base + offs.o[j];
+  cplx* d = dst.p[j];
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x) d[e] = s[e];
+}
+
+// ---- overlaps ----
+__device__ __forceinline__ const cplx* side_site(const OvlSide& s, int z, int site) {
+  return s.use_ptrs ? s.ptrs.p[site] : s.base + (long long)(s.slot0 + z) * s.slot_stride + s.offs.o[site];
+}
+__device__ __forceinline__ const int* side_dims(const OvlSide& s, int z) {
+  return s.dims + (long long)(s.use_ptrs ? 0 : (s.slot0 + z)) * s.dims_stride;
+}
+
+// Per batch entry z and site j: T = E . B_j   (nE*chiA x D*chiB')   and  E'_c = A_j^H . T_c  for c < nE.
+// descs layout: [0*batch + z] the T gemm, [(1+c)*batch + z] the E' gemms.
+__global__ void overlap_plan_kernel(GemmDesc* descs, OvlSide bra, OvlSide ket, int site, int batch, int D, int withK, cplx* E_in,
+                                    cplx* E_out, cplx* T, long long e_stride, long long t_stride) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= batch) return;
+  const int* da = side_dims(bra, z);
+  const int* db = side_dims(ket, z);
+  const int aL = da[site], aR = da[site + 1], bL = db[site], bR = db[site + 1];
+  const int nE = withK ? 2 : 1;
+  const cplx* A = side_site(bra, z, site);
+  const cplx* B = side_site(ket, z, site);
+  cplx* Ei = E_in + z * e_stride;
+  cplx* Eo = E_out + z * e_stride;
+  cplx* Tz = T + z * t_stride;
+  GemmDesc g;
+  g.pad = 0;
+  // T (nE*aL x D*bR) = E (nE*aL x bL) . B (bL x D*bR)
+  g.A = Ei; g.opA = 0; g.lda = bL;
+  g.B = B; g.opB = 0; g.ldb = D * bR;
+  g.C = Tz; g.ldc = D * bR; g.M = nE * aL; g.N = D * bR; g.K = bL;
+  descs[z] = g;
+  for (int c = 0; c < nE; ++c) {
+    // E'_c (aR x bR) = A^H (aL*D x aR)^H . T_c (aL*D x bR)
+    g.A = A; g.opA = 1; g.lda = aR;
+    g.B = Tz + (long long)c * aL * D * bR; g.opB = 0; g.ldb = bR;
+    g.C = Eo + (long long)c * aR * bR; g.ldc = bR; g.M = aR; g.N = bR; g.K = aL * D;
+    descs[(1 + c) * batch + z] = g;
+  }
+}
+
+__global__ void overlap_init_kernel(cplx* E, long long e_stride, int batch, int withK) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= batch) return;
+  E[z * e_stride] = make_double2(1.0, 0.0);
+  if (withK) E[z * e_stride + 1] = make_double2(0.0, 0.0);
+}
+
+// T1 += k_s T0 with k_s = s(s-1)/2 (src/BH_tDMRG.cpp:10-14); T is [c][l][s][r]
+__global__ void overlap_kfix_kernel(cplx* T, long long t_stride, const GemmDesc* descs, int D) {
+  const int z = blockIdx.y;
+  const GemmDesc g = descs[z];
+  const int aL = g.M / 2, N = g.N;       // N = D*bR
+  const int bR = N / D;
+  cplx* T0 = T + z * t_stride;
+  cplx* T1 = T0 + (long long)aL * N;
+  const long long total = (long long)aL * N;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)((e % N) / bR);
+    const double k = 0.5 * s * (s - 1);
+    if (k != 0.0) {
+      cplx a = T0[e], b = T1[e];
+      T1[e] = make_double2(b.x + k * a.x, b.y + k * a.y);
+    }
+  }
+}
+
+__global__ void overlap_final_kernel(const cplx* E, long long e_stride, int batch, int withK, cplx* out) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= batch) return;
+  out[z] = E[z * e_stride + (withK ? 1 : 0)];
+}
+
+// ---- K|psi>: B[(l,a), s, (r,b)] = A[l,s,r] W[a,b,s], W = [[1,0],[k_s,1]], boundaries pick row 1 / column 0 ----
+__global__ void applyK_expand_kernel(const cplx* A, cplx* B, const int* dimL_in, const int* dimR_in, const int* qL_in,
+                                     const int* qR_in, int* dimL_out, int* dimR_out, int* qL_out, int* qR_out, int D, int site,
+                                     int L) {
+  const int chiL = *dimL_in, chiR = *dimR_in;
+  const int nA = (site == 0) ? 1 : 2, nB = (site == L - 1) ? 1 : 2;
+  const int oL = chiL * nA, oR = chiR * nB;
+  const long long total = (long long)oL * D * oR;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int rb = (int)(e % oR);
+    const int s = (int)((e / oR) % D);
+    const int la = (int)(e / ((long long)oR * D));
+    const int l = la / nA, a0 = la % nA, r = rb / nB, b0 = rb % nB;
+    const int a = (site == 0) ? 1 : a0;            // left boundary: row 1
+    const int b = (site == L - 1) ? 0 : b0;        // right boundary: column 0
+    double w = 0.0;
+    if (a == b) w = 1.0;
+    else if (a == 1 && b == 0) w = 0.5 * s * (s - 1);
+    const cplx u = A[((long long)l * D + s) * chiR + r];
+    B[e] = make_double2(u.x * w, u.y * w);
+  }
+  if (blockIdx.x == 0) {
+    // bookkeeping of the right bond (and the left bond on the first site)
+    for (int i = threadIdx.x; i < oR; i += blockDim.x) qR_out[i] = qR_in[i / nB];
+    if (site == 0) for (int i = threadIdx.x; i < oL; i += blockDim.x) qL_out[i] = qL_in[i / nA];
+    if (threadIdx.x == 0) { *dimR_out = oR; if (site == 0) *dimL_out = oL; }
+  }
+}
+
+}  // namespace
+
+void launch_merge_setup(GemmDesc* d, const cplx* A1, const cplx* A2, cplx* theta, const int* dimL, const int* dimM,
+                        const int* dimR, int D, cudaStream_t s) {
+  merge_setup_kernel<<<1, 32, 0, s>>>(d, A1, A2, theta, dimL, dimM, dimR, D);
+}
+
+void launch_gate_apply(cplx* theta, const int* dimL, const int* dimR, int D, const cplx* G, Phases ph, int maxL, int maxR,
+                       cudaStream_t s) {
+  const int grid = grid_for((long long)maxL * maxR, 128);
+  const size_t sm = sizeof(cplx) * D * D * D * D;
+  static bool attr8 = false;
+  if (D == 8 && !attr8) {
+    cudaFuncSetAttribute(gate_apply_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    attr8 = true;
+  }
+  switch (D) {
+    case 2: gate_apply_kernel<2><<<grid, 128, sm, s>>>(theta, dimL, dimR, G, ph); break;
+    case 3: gate_apply_kernel<3><<<grid, 128, sm, s>>>(theta, dimL, dimR, G, ph); break;
+    case 4: gate_apply_kernel<4><<<grid, 128, sm, s>>>(theta, dimL, dimR, G, ph); break;
+    case 5: gate_apply_kernel<5><<<grid, 128, sm, s>>>(theta, dimL, dimR, G, ph); break;
+    case 6: gate_apply_kernel<6><<<grid, 128, sm, s>>>(theta, dimL, dimR, G, ph); break;
+    case 7: gate_apply_kernel<7><<<grid, 128, sm, s>>>(theta, dimL, dimR, G, ph); break;
+    case 8: gate_apply_kernel<8><<<grid, 128, sm, s>>>(theta, dimL, dimR, G, ph); break;
+    default: break;
+  }
+}
+
+void launch_site_phase(cplx* A, const int* dimL, const int* dimR, int D, Phases ph, int which, int max_elems, cudaStream_t s) {
+  site_phase_kernel<<<grid_for(max_elems, 256), 256, 0, s>>>(A, dimL, dimR, D, ph, which);
+}
+
+void launch_pack_copy(SitePtrs src, cplx* dst_base, SiteOffs offs, const int* dims, int L, int D, int max_site_elems,
+                      cudaStream_t s) {
+  dim3 grid(grid_for(max_site_elems, 256, 64), L);
+  pack_copy_kernel<<<grid, 256, 0, s>>>(src, dst_base, offs, dims, D);
+}
+void launch_unpack_copy(const cplx* src_base, SitePtrs dst, SiteOffs offs, const int* dims, int L, int D, int max_site_elems,
+                        cudaStream_t s) {
+  dim3 grid(grid_for(max_site_elems, 256, 64), L);
+  unpack_copy_kernel<<<grid, 256, 0, s>>>(src_base, dst, offs, dims, D);
+}
+
+void launch_overlap_plan(GemmDesc* descs, const OvlSide& bra, const OvlSide& ket, int site, int batch, int D, int withK,
+                         cplx* E_in, cplx* E_out, cplx* T, long long e_stride, long long t_stride, cudaStream_t s) {
+  overlap_plan_kernel<<<(batch + 63) / 64, 64, 0, s>>>(descs, bra, ket, site, batch, D, withK, E_in, E_out, T, e_stride, t_stride);
+}
+void launch_overlap_init(cplx* E, long long e_stride, int batch, int withK, cudaStream_t s) {
+  overlap_init_kernel<<<(batch + 63) / 64, 64, 0, s>>>(E, e_stride, batch, withK);
+}
+void launch_overlap_kfix(cplx* T, long long t_stride, const GemmDesc* descs, int batch, int D, int max_elems, cudaStream_t s) {
+  dim3 grid(grid_for(max_elems, 256, 32), batch);
+  overlap_kfix_kernel<<<grid, 256, 0, s>>>(T, t_stride, descs, D);
+}
+void launch_overlap_final(const cplx* E, long long e_stride, int batch, int withK, cplx* out, cudaStream_t s) {
+  overlap_final_kernel<<<(batch + 63) / 64, 64, 0, s>>>(E, e_stride, batch, withK, out);
+}
+
+void launch_applyK_expand(const cplx* A, cplx* B, const int* dimL_in, const int* dimR_in, const int* qL_in, const int* qR_in,
+                          int* dimL_out, int* dimR_out, int* qL_out, int* qR_out, int D, int site, int L, int max_elems,
+                          cudaStream_t s) {
+  applyK_expand_kernel<<<grid_for(max_elems, 256), 256, 0, s>>>(A, B, dimL_in, dimR_in, qL_in, qR_in, dimL_out, dimR_out,
+                                                                 qL_out, qR_out, D, site, L);
+}

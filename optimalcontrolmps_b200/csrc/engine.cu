@@ -1,0 +1,1242 @@
+// Host orchestration of libocmps and its C ABI (include/ocmps.h).
+//
+// A Trotter step is a fixed, data-independent list of operations (phase, two-site gate +
+// truncating decomposition, gauge move, normalise) derived from the chain length exactly the
+// way BH_tDMRG::doStep walks its gate list (reference src/BH_tDMRG.cpp:127-230, including
+// ITensor's orthogonality-limit bookkeeping).  All data-dependent sizes stay on the GPU, so a
+// whole sweep is enqueued without host synchronisation; independent chains (psi sweep, xi
+// sweep, Hessian rows) run on their own streams.
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "ocmps_internal.h"
+#include "../../include/ocmps.h"
+
+long long g_ocmps_launches = 0;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return fail(OCMPS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));              \
+  } while (0)
+
+constexpr double MIN_CUT = 1e-16;   // ITensor default Cutoff
+constexpr int MAX_M = 5000;         // ITensor default Maxm
+constexpr int NV_MAX = 2048;        // must match decomp.cu
+constexpr size_t JAC_SMEM_LIMIT = 200 * 1024;
+
+struct Layout {
+  int L = 0, D = 0, cap = 0;
+  int capb[OCMPS_MAX_L + 1];
+  SiteOffs offs;
+  long long total = 0;
+  int max_site_elems = 0;
+  // mult = 2 for the intermediate K|psi> product whose bonds are twice those of a chi_cap MPS
+  void init(int L_, int D_, int cap_, int mult = 1) {
+    L = L_; D = D_; cap = cap_ * mult;
+    for (int b = 0; b <= L; ++b) {
+      int e = std::min(b, L - b);
+      long long v = 1;
+      for (int i = 0; i < e && v < cap_; ++i) v *= D;
+      capb[b] = (int)std::min<long long>(v, cap_) * ((b == 0 || b == L) ? 1 : mult);
+    }
+    total = 0; max_site_elems = 0;
+    for (int j = 0; j < L; ++j) {
+      offs.o[j] = total;
+      long long n = (long long)capb[j] * D * capb[j + 1];
+      max_site_elems = std::max<long long>(max_site_elems, n);
+      total += n;
+    }
+    offs.o[L] = total;
+  }
+};
+
+}  // namespace
+
+struct ocmps_ctx {
+  int dev = 0;
+  int* d_status = nullptr;
+  cudaStream_t stream0 = nullptr;
+  std::vector<struct Workspace*> pool;
+};
+
+struct ocmps_mps {
+  ocmps_ctx* ctx = nullptr;
+  Layout lay;
+  cplx* arena[2] = {nullptr, nullptr};
+  int cur[OCMPS_MAX_L];
+  int* d_dims = nullptr;
+  int* d_q = nullptr;       // (L+1) x cap
+  int llim = 0, rlim = 2;
+  cplx* site(int j) const { return arena[cur[j]] + lay.offs.o[j]; }
+  cplx* other(int j) const { return arena[1 - cur[j]] + lay.offs.o[j]; }
+  int* dim(int b) const { return d_dims + b; }
+  int* q(int b) const { return d_q + (size_t)b * lay.cap; }
+  SitePtrs ptrs() const {
+    SitePtrs p;
+    for (int j = 0; j < lay.L; ++j) p.p[j] = site(j);
+    return p;
+  }
+};
+
+struct ocmps_store {
+  ocmps_ctx* ctx = nullptr;
+  Layout lay;
+  int nslots = 0;
+  cplx* data = nullptr;
+  int* dims = nullptr;     // nslots x (L+1)
+  int* q = nullptr;        // nslots x (L+1) x cap
+};
+
+namespace {
+
+struct Op {
+  int kind;    // 0 phase, 1 gate, 2 orth, 3 normalise
+  int a, b, c; // phase: site(1-based), which(0: U1 / 1: U2), -; gate: i1, gate_kind(0 left,1 left+U2 on last,2 right), dir(0 left,1 right);
+               // orth: bond b (sites b,b+1), dir; normalise: site
+};
+
+}  // namespace
+
+struct Workspace {
+  ocmps_ctx* ctx = nullptr;
+  int L = 0, D = 0, cap = 0;
+  cudaStream_t stream = nullptr;
+  cplx* theta = nullptr;
+  cplx* cbuf = nullptr;
+  DecompBuffers db;
+  // overlaps
+  cplx* E[2] = {nullptr, nullptr};
+  cplx* T = nullptr;
+  GemmDesc* odescs = nullptr;
+  cplx* d_out = nullptr;       // overlap results (device)
+  int obatch = 0;
+  long long e_stride = 0, t_stride = 0;
+  // work states
+  ocmps_mps* work = nullptr;
+  ocmps_mps* big = nullptr;    // 2*cap bonds, for K|psi>
+  Workspace* bigws = nullptr;  // decomposition buffers for 2*cap
+  double* d_norm = nullptr;    // scalar outputs
+};
+
+struct ocmps_stepper {
+  ocmps_ctx* ctx = nullptr;
+  int L = 0, D = 0, cap = 0;
+  double J = 1.0, tstep = 0.0;
+  bool has_cutoff = false, has_maxm = false;
+  double cutoff = MIN_CUT;
+  int maxm = MAX_M;
+  int rel_cutoff = 0;
+  cplx* d_G[2] = {nullptr, nullptr};     // [0] forward, [1] backward
+  std::vector<std::complex<double>> h_G[2];
+  std::vector<Op> ops;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// allocation helpers
+// ------------------------------------------------------------------------------------------------
+int alloc_mps(ocmps_ctx* ctx, int L, int D, int cap, ocmps_mps** out, int mult = 1) {
+  if (L < 1 || L > OCMPS_MAX_L) return fail(OCMPS_ERR_INVALID, "L out of range [1,64]");
+  if (D < 2 || D > OCMPS_MAX_D) return fail(OCMPS_ERR_INVALID, "D out of range [2,8]");
+  if (cap < 1 || (long long)cap * mult * D > NV_MAX) return fail(OCMPS_ERR_INVALID, "chi_cap*D exceeds 2048");
+  ocmps_mps* m = new ocmps_mps();
+  m->ctx = ctx;
+  m->lay.init(L, D, cap, mult);
+  cap = m->lay.cap;
+  CK(cudaSetDevice(ctx->dev));
+  CK(cudaMalloc(&m->arena[0], sizeof(cplx) * m->lay.total));
+  CK(cudaMalloc(&m->arena[1], sizeof(cplx) * m->lay.total));
+  CK(cudaMalloc(&m->d_dims, sizeof(int) * (L + 1)));
+  CK(cudaMalloc(&m->d_q, sizeof(int) * (size_t)(L + 1) * cap));
+  CK(cudaMemset(m->d_dims, 0, sizeof(int) * (L + 1)));
+  CK(cudaMemset(m->d_q, 0, sizeof(int) * (size_t)(L + 1) * cap));
+  for (int j = 0; j < L; ++j) m->cur[j] = 0;
+  *out = m;
+  return OCMPS_OK;
+}
+
+void free_mps(ocmps_mps* m) {
+  if (!m) return;
+  cudaFree(m->arena[0]); cudaFree(m->arena[1]); cudaFree(m->d_dims); cudaFree(m->d_q);
+  delete m;
+}
+
+int alloc_ws(ocmps_ctx* ctx, int L, int D, int cap, bool with_work, Workspace** out) {
+  Workspace* w = new Workspace();
+  w->ctx = ctx; w->L = L; w->D = D; w->cap = cap;
+  CK(cudaSetDevice(ctx->dev));
+  CK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+  const size_t nD = (size_t)cap * D;
+  CK(cudaMalloc(&w->theta, sizeof(cplx) * nD * nD));
+  CK(cudaMalloc(&w->cbuf, sizeof(cplx) * (size_t)cap * cap));
+  CK(cudaMalloc(&w->db.dw, sizeof(DecompWork)));
+  CK(cudaMalloc(&w->db.vec_idx, sizeof(int) * NV_MAX));
+  CK(cudaMalloc(&w->db.comp_idx, sizeof(int) * 3 * NV_MAX));
+  CK(cudaMalloc(&w->db.vecq, sizeof(int) * NV_MAX));
+  CK(cudaMalloc(&w->db.P, sizeof(double) * NV_MAX));
+  CK(cudaMalloc(&w->db.pos, sizeof(int) * 3 * NV_MAX));
+  CK(cudaMalloc(&w->db.ywork, sizeof(cplx) * nD * cap));
+  CK(cudaMalloc(&w->db.descs, sizeof(GemmDesc) * 4));
+  CK(cudaMalloc(&w->db.partial, sizeof(double) * 64));
+  CK(cudaMalloc(&w->d_norm, sizeof(double) * 4));
+  w->db.status = ctx->d_status;
+  if (with_work) {
+    int rc = alloc_mps(ctx, L, D, cap, &w->work);
+    if (rc) return rc;
+  }
+  *out = w;
+  return OCMPS_OK;
+}
+
+int ensure_overlap_bufs(Workspace* w, int batch, int capA, int capB) {
+  const long long es = 2LL * capA * capB, ts = 2LL * capA * w->D * capB;
+  if (w->obatch >= batch && w->e_stride >= es && w->t_stride >= ts) return OCMPS_OK;
+  cudaFree(w->E[0]); cudaFree(w->E[1]); cudaFree(w->T); cudaFree(w->odescs); cudaFree(w->d_out);
+  w->obatch = std::max(batch, w->obatch);
+  w->e_stride = std::max(es, w->e_stride); w->t_stride = std::max(ts, w->t_stride);
+  CK(cudaMalloc(&w->E[0], sizeof(cplx) * w->e_stride * w->obatch));
+  CK(cudaMalloc(&w->E[1], sizeof(cplx) * w->e_stride * w->obatch));
+  CK(cudaMalloc(&w->T, sizeof(cplx) * w->t_stride * w->obatch));
+  CK(cudaMalloc(&w->odescs, sizeof(GemmDesc) * 3 * w->obatch));
+  CK(cudaMalloc(&w->d_out, sizeof(cplx) * w->obatch));
+  return OCMPS_OK;
+}
+
+void free_ws(Workspace* w) {
+  if (!w) return;
+  cudaFree(w->theta); cudaFree(w->cbuf); cudaFree(w->db.dw); cudaFree(w->db.vec_idx); cudaFree(w->db.comp_idx);
+  cudaFree(w->db.vecq); cudaFree(w->db.P); cudaFree(w->db.pos); cudaFree(w->db.ywork); cudaFree(w->db.descs);
+  cudaFree(w->db.partial); cudaFree(w->d_norm);
+  cudaFree(w->E[0]); cudaFree(w->E[1]); cudaFree(w->T); cudaFree(w->odescs); cudaFree(w->d_out);
+  free_mps(w->work); free_mps(w->big);
+  if (w->bigws) free_ws(w->bigws);
+  if (w->stream) cudaStreamDestroy(w->stream);
+  delete w;
+}
+
+// workspace number `idx` for the given shape (created on demand, owned by the context)
+int get_ws(ocmps_ctx* ctx, int L, int D, int cap, int idx, Workspace** out) {
+  int seen = 0;
+  for (Workspace* w : ctx->pool) {
+    if (w->L == L && w->D == D && w->cap == cap) {
+      if (seen == idx) { *out = w; return OCMPS_OK; }
+      ++seen;
+    }
+  }
+  while (seen <= idx) {
+    Workspace* w = nullptr;
+    int rc = alloc_ws(ctx, L, D, cap, true, &w);
+    if (rc) return rc;
+    ctx->pool.push_back(w);
+    *out = w;
+    ++seen;
+  }
+  return OCMPS_OK;
+}
+
+int check_status(ocmps_ctx* ctx) {
+  int st = 0;
+  CK(cudaMemcpy(&st, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+  if (st) {
+    cudaMemset(ctx->d_status, 0, sizeof(int));
+    std::string msg = "device status:";
+    if (st & OCMPS_ST_CAPACITY) msg += " bond dimension exceeds chi_cap;";
+    if (st & OCMPS_ST_NOCONV) msg += " Jacobi did not converge;";
+    if (st & OCMPS_ST_CHARGE) msg += " charge label >= 256;";
+    if (st & OCMPS_ST_TOOMANYBLK) msg += " more than 128 charge blocks;";
+    return fail((st & OCMPS_ST_CAPACITY) ? OCMPS_ERR_CAPACITY : OCMPS_ERR_NUMERIC, msg);
+  }
+  return OCMPS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gates (BondGate) and the op schedule (src/BH_tDMRG.cpp:127-230)
+// ------------------------------------------------------------------------------------------------
+typedef std::complex<double> zc;
+
+std::vector<zc> bond_gate(int D, double J, double tau) {
+  const int n = D * D;
+  std::vector<zc> h(n * n, 0.0), unit(n * n, 0.0), term, gate, x(n * n);
+  // h[(t1,t2),(s1,s2)] = -J (A x Adag + Adag x A); <j-1|A|j> = sqrt(j)   (BH_sites.h:136-148)
+  auto Aop = [&](int t, int s) { return (s == t + 1) ? std::sqrt((double)s) : 0.0; };
+  auto Adop = [&](int t, int s) { return (t == s + 1) ? std::sqrt((double)t) : 0.0; };
+  for (int t1 = 0; t1 < D; ++t1) for (int t2 = 0; t2 < D; ++t2)
+    for (int s1 = 0; s1 < D; ++s1) for (int s2 = 0; s2 < D; ++s2)
+      h[(t1 * D + t2) * n + s1 * D + s2] = -J * (Aop(t1, s1) * Adop(t2, s2) + Adop(t1, s1) * Aop(t2, s2));
+  for (int i = 0; i < n; ++i) unit[i * n + i] = 1.0;
+  for (int i = 0; i < n * n; ++i) x[i] = h[i] * zc(0.0, -tau);
+  term = x;
+  gate = unit;
+  std::vector<zc> tmp(n * n);
+  for (int ord = 100; ord >= 1; --ord) {       // Horner form of the Taylor series
+    for (int i = 0; i < n * n; ++i) { term[i] /= (double)ord; gate[i] = unit[i] + term[i]; }
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        zc s = 0.0;
+        for (int k = 0; k < n; ++k) s += gate[i * n + k] * x[k * n + j];
+        tmp[i * n + j] = s;
+      }
+    term = tmp;
+  }
+  return gate;
+}
+
+struct Limits {
+  int l = 0, r = 2;
+  void touch(int i) { if (l > i - 1) l = i - 1; if (r < i + 1) r = i + 1; }
+};
+
+void emit_position(std::vector<Op>& ops, Limits& lim, int i, int L) {
+  while (lim.l < i - 1) {
+    if (lim.l < 0) lim.l = 0;
+    ops.push_back({2, lim.l + 1, 0, 0});
+    ++lim.l;
+    if (lim.r < lim.l + 2) lim.r = lim.l + 2;
+  }
+  while (lim.r > i + 1) {
+    if (lim.r > L + 1) lim.r = L + 1;
+    ops.push_back({2, lim.r - 2, 1, 0});
+    --lim.r;
+    if (lim.l > lim.r - 2) lim.l = lim.r - 2;
+  }
+}
+
+std::vector<Op> build_schedule(int L) {
+  std::vector<Op> ops;
+  std::vector<std::pair<int, int>> gates;
+  for (int i = 1; i < L; i += 2) gates.push_back({i, i + 1});           // :28-38
+  const int offset = (L % 2 == 0) ? 2 : 1;
+  for (int i = L - offset; i >= 1; i -= 2) gates.push_back({i, i + 1}); // :45-57
+  Limits lim;                       // centre at site 1
+  if (L % 2 != 0) {                 // :133-136
+    lim.touch(L);
+    ops.push_back({0, L, 0, 0});
+  }
+  bool from_left = true;
+  for (size_t gi = 0; gi < gates.size(); ++gi) {
+    const int i1 = gates[gi].first, i2 = gates[gi].second;
+    lim.touch(i1); lim.touch(i2);
+    const int gk = from_left ? ((i2 == L && L % 2 == 0) ? 1 : 0) : 2;
+    if (gi + 1 < gates.size()) {
+      const int ni1 = gates[gi + 1].first, ni2 = gates[gi + 1].second;
+      if (ni1 >= i2) {              // :173-188
+        ops.push_back({1, i1, gk, 0});
+        lim.l = i1;
+        if (lim.r < i1 + 2) lim.r = i1 + 2;
+        lim.touch(i1 + 1);
+        emit_position(ops, lim, ni1, L);
+      }
+      if (ni1 < i2) {               // :189-199
+        ops.push_back({1, i1, gk, 1});
+        if (lim.l > i1 - 1) lim.l = i1 - 1;
+        lim.r = i1 + 1;
+        lim.touch(i1);
+        emit_position(ops, lim, ni2, L);
+      }
+      if (i2 == ni1 || i1 == ni2) from_left = false;   // :200-204
+    } else {                        // :206-218
+      ops.push_back({1, i1, gk, 1});
+      lim.l = i1 - 1;
+      lim.r = i1 + 1;
+      lim.touch(i1);
+      emit_position(ops, lim, 1, L);
+    }
+  }
+  lim.touch(1);
+  ops.push_back({0, 1, 1, 0});      // :222-223
+  ops.push_back({3, 1, 0, 0});      // :228
+  return ops;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decomposition driver
+// ------------------------------------------------------------------------------------------------
+void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int capV, int capC, int maxIso, cudaStream_t s) {
+  launch_decomp_setup(a, ws->db, s);
+  // shared memory: the largest block has at most capV vectors of at most capC components
+  size_t need = (size_t)capV * capC * sizeof(cplx);
+  size_t smem = std::min(need, JAC_SMEM_LIMIT);
+  if (smem < 1024) smem = 1024;
+  int nblk = std::min(OCMPS_MAX_BLK, std::max(capV, capC) + a.D);
+  launch_jacobi_blocks(a, ws->db, nblk, smem, s);
+  launch_truncate(a, ws->db, tp, s);
+  launch_scatter_iso(a, ws->db, maxIso, s);
+  g_ocmps_launches += 4;
+}
+
+void phases_of(int D, double U, double tstep, double* re, double* im) {
+  for (int n = 0; n < D; ++n) {
+    const double ang = -0.25 * U * tstep * (double)n * (double)(n - 1);   // src/BH_tDMRG.cpp:87-88
+    re[n] = std::cos(ang);
+    im[n] = std::sin(ang);
+  }
+}
+
+// one Trotter step in place on `m`, enqueued on `s`
+void run_step(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, double from, double to, bool forward, cudaStream_t s,
+              int op_begin = 0, int op_end = 1 << 30) {
+  const int L = st->L, D = st->D;
+  const Layout& lay = m->lay;
+  double u1r[OCMPS_MAX_D], u1i[OCMPS_MAX_D], u2r[OCMPS_MAX_D], u2i[OCMPS_MAX_D];
+  phases_of(D, forward ? from : -from, st->tstep, u1r, u1i);   // :116-123
+  phases_of(D, forward ? to : -to, st->tstep, u2r, u2i);
+  const cplx* G = st->d_G[forward ? 0 : 1];
+  TruncParams tpg{st->cutoff, st->maxm, 1, st->rel_cutoff, 0};
+  TruncParams tpo{MIN_CUT, MAX_M, 1, 0, 0};
+
+  for (int oi = op_begin; oi < (int)st->ops.size() && oi < op_end; ++oi) {
+    const Op& op = st->ops[oi];
+    if (op.kind == 0) {
+      const int j = op.a - 1;
+      Phases ph;
+      for (int n = 0; n < D; ++n) {
+        ph.re[0][n] = op.b == 0 ? u1r[n] : u2r[n];
+        ph.im[0][n] = op.b == 0 ? u1i[n] : u2i[n];
+      }
+      launch_site_phase(m->site(j), m->dim(j), m->dim(j + 1), D, ph, 0, lay.capb[j] * D * lay.capb[j + 1], s);
+      g_ocmps_launches += 1;
+    } else if (op.kind == 1) {
+      const int j1 = op.a - 1, j2 = op.a;                 // 0-based sites
+      const int bl = j1, bm = j1 + 1, br = j2 + 1;        // bonds
+      launch_merge_setup(ws->db.descs + 2, m->site(j1), m->site(j2), ws->theta, m->dim(bl), m->dim(bm), m->dim(br), D, s);
+      launch_zgemm(ws->db.descs + 2, 1, lay.capb[bl] * D, D * lay.capb[br], s);
+      Phases ph;
+      for (int n = 0; n < D; ++n) {
+        for (int k = 0; k < 4; ++k) { ph.re[k][n] = 1.0; ph.im[k][n] = 0.0; }
+        if (op.b == 0 || op.b == 1) {                       // U(from) before the J gate (:150)
+          ph.re[0][n] = ph.re[1][n] = u1r[n]; ph.im[0][n] = ph.im[1][n] = u1i[n];
+          if (op.b == 1) { ph.re[3][n] = u2r[n]; ph.im[3][n] = u2i[n]; }   // lonely U(to) on the last site (:153-155)
+        } else {                                            // J gate first, then U(to) (:159)
+          ph.re[2][n] = ph.re[3][n] = u2r[n]; ph.im[2][n] = ph.im[3][n] = u2i[n];
+        }
+      }
+      launch_gate_apply(ws->theta, m->dim(bl), m->dim(br), D, G, ph, lay.capb[bl], lay.capb[br], s);
+      DecompArgs a;
+      a.kind = op.c == 0 ? DK_GATE_LEFT : DK_GATE_RIGHT;
+      a.D = D;
+      a.dimL = m->dim(bl); a.dimR = m->dim(br); a.qL = m->q(bl); a.qR = m->q(br);
+      a.dimNew = m->dim(bm); a.qNew = m->q(bm);
+      a.X = ws->theta;
+      a.iso = op.c == 0 ? m->other(j1) : m->other(j2);
+      a.partner = op.c == 0 ? m->other(j2) : m->other(j1);
+      a.nb_in = nullptr; a.nb_out = nullptr; a.dimNb = nullptr;
+      tpg.cap = lay.capb[bm];
+      const int n_cap = lay.capb[bl] * D, m_cap = D * lay.capb[br];
+      // vectors per block <= chi of their own side, components <= chi of the other side
+      const int capV = op.c == 0 ? lay.capb[br] : lay.capb[bl];
+      const int capC = op.c == 0 ? lay.capb[bl] : lay.capb[br];
+      run_decomp(ws, a, tpg, capV, capC, (op.c == 0 ? n_cap : m_cap) * lay.capb[bm], s);
+      if (op.c == 0) launch_zgemm(ws->db.descs, 1, lay.capb[bm], m_cap, s);
+      else launch_zgemm(ws->db.descs, 1, n_cap, lay.capb[bm], s);
+      launch_normalize(a.partner, ws->db, (op.c == 0 ? m_cap : n_cap) * lay.capb[bm], s);   // :183-184,195-196
+      m->cur[j1] ^= 1; m->cur[j2] ^= 1;
+      g_ocmps_launches += 6;
+    } else if (op.kind == 2) {
+      const int b = op.a;                                  // bond between sites b and b+1 (1-based) = bond index b
+      DecompArgs a;
+      a.D = D;
+      a.dimNew = m->dim(b); a.qNew = m->q(b);
+      a.partner = ws->cbuf;
+      tpo.cap = lay.capb[b];
+      if (op.b == 0) {            // left: SVD of site b (0-based b-1), S.V pushed into site b+1
+        const int j = b - 1, jn = b;
+        a.kind = DK_ORTH_LEFT;
+        a.dimL = m->dim(b - 1); a.dimR = m->dim(b); a.qL = m->q(b - 1); a.qR = m->q(b);
+        a.X = m->site(j); a.iso = m->other(j);
+        a.nb_in = m->site(jn); a.nb_out = m->other(jn); a.dimNb = m->dim(b + 1);
+        run_decomp(ws, a, tpo, lay.capb[b], lay.capb[b - 1], lay.capb[b - 1] * D * lay.capb[b], s);
+        launch_zgemm(ws->db.descs, 1, lay.capb[b], lay.capb[b], s);
+        launch_zgemm(ws->db.descs + 1, 1, lay.capb[b], D * lay.capb[b + 1], s);
+        m->cur[j] ^= 1; m->cur[jn] ^= 1;
+      } else {                    // right: SVD of site b+1 (0-based b), U.S pushed into site b
+        const int j = b, jn = b - 1;
+        a.kind = DK_ORTH_RIGHT;
+        a.dimL = m->dim(b); a.dimR = m->dim(b + 1); a.qL = m->q(b); a.qR = m->q(b + 1);
+        a.X = m->site(j); a.iso = m->other(j);
+        a.nb_in = m->site(jn); a.nb_out = m->other(jn); a.dimNb = m->dim(b - 1);
+        run_decomp(ws, a, tpo, lay.capb[b], lay.capb[b + 1], lay.capb[b] * D * lay.capb[b + 1], s);
+        launch_zgemm(ws->db.descs, 1, lay.capb[b], lay.capb[b], s);
+        launch_zgemm(ws->db.descs + 1, 1, lay.capb[b - 1] * D, lay.capb[b], s);
+        m->cur[j] ^= 1; m->cur[jn] ^= 1;
+      }
+      g_ocmps_launches += 2;
+    } else {
+      const int j = op.a - 1;
+      launch_normalize_site(m->site(j), m->dim(j), m->dim(j + 1), D, ws->db.partial, lay.capb[j] * D * lay.capb[j + 1], s);
+      g_ocmps_launches += 2;
+    }
+  }
+  if (op_end >= (int)st->ops.size()) { m->llim = 0; m->rlim = 2; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// copies
+// ------------------------------------------------------------------------------------------------
+int copy_mps_async(ocmps_mps* dst, ocmps_mps* src, cudaStream_t s) {
+  if (dst->lay.L != src->lay.L || dst->lay.D != src->lay.D || dst->lay.cap != src->lay.cap)
+    return fail(OCMPS_ERR_INVALID, "mps copy: shape mismatch");
+  const Layout& lay = src->lay;
+  launch_pack_copy(src->ptrs(), dst->arena[0], lay.offs, src->d_dims, lay.L, lay.D, lay.max_site_elems, s);
+  g_ocmps_launches += 1;
+  for (int j = 0; j < lay.L; ++j) dst->cur[j] = 0;
+  CK(cudaMemcpyAsync(dst->d_dims, src->d_dims, sizeof(int) * (lay.L + 1), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(dst->d_q, src->d_q, sizeof(int) * (size_t)(lay.L + 1) * lay.cap, cudaMemcpyDeviceToDevice, s));
+  dst->llim = src->llim; dst->rlim = src->rlim;
+  return OCMPS_OK;
+}
+
+int store_put_async(ocmps_store* st, int slot, ocmps_mps* m, cudaStream_t s) {
+  const Layout& lay = st->lay;
+  if (m->lay.L != lay.L || m->lay.D != lay.D || m->lay.cap != lay.cap) return fail(OCMPS_ERR_INVALID, "store/mps shape mismatch");
+  if (slot < 0 || slot >= st->nslots) return fail(OCMPS_ERR_INVALID, "slot out of range");
+  launch_pack_copy(m->ptrs(), st->data + (size_t)slot * lay.total, lay.offs, m->d_dims, lay.L, lay.D, lay.max_site_elems, s);
+  g_ocmps_launches += 1;
+  CK(cudaMemcpyAsync(st->dims + (size_t)slot * (lay.L + 1), m->d_dims, sizeof(int) * (lay.L + 1), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(st->q + (size_t)slot * (lay.L + 1) * lay.cap, m->d_q, sizeof(int) * (size_t)(lay.L + 1) * lay.cap,
+                     cudaMemcpyDeviceToDevice, s));
+  return OCMPS_OK;
+}
+
+int store_get_async(ocmps_store* st, int slot, ocmps_mps* m, cudaStream_t s) {
+  const Layout& lay = st->lay;
+  if (m->lay.L != lay.L || m->lay.D != lay.D || m->lay.cap != lay.cap) return fail(OCMPS_ERR_INVALID, "store/mps shape mismatch");
+  if (slot < 0 || slot >= st->nslots) return fail(OCMPS_ERR_INVALID, "slot out of range");
+  for (int j = 0; j < lay.L; ++j) m->cur[j] = 0;
+  const int* dims = st->dims + (size_t)slot * (lay.L + 1);
+  launch_unpack_copy(st->data + (size_t)slot * lay.total, m->ptrs(), lay.offs, dims, lay.L, lay.D, lay.max_site_elems, s);
+  g_ocmps_launches += 1;
+  CK(cudaMemcpyAsync(m->d_dims, dims, sizeof(int) * (lay.L + 1), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(m->d_q, st->q + (size_t)slot * (lay.L + 1) * lay.cap, sizeof(int) * (size_t)(lay.L + 1) * lay.cap,
+                     cudaMemcpyDeviceToDevice, s));
+  m->llim = 0; m->rlim = 2;
+  return OCMPS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// overlaps
+// ------------------------------------------------------------------------------------------------
+OvlSide side_of_mps(const ocmps_mps* m) {
+  OvlSide s;
+  s.base = nullptr; s.slot_stride = 0; s.offs = m->lay.offs; s.ptrs = m->ptrs();
+  s.dims = m->d_dims; s.dims_stride = 0; s.use_ptrs = 1; s.slot0 = 0;
+  return s;
+}
+OvlSide side_of_store(const ocmps_store* st, int slot0) {
+  OvlSide s;
+  s.base = st->data; s.slot_stride = st->lay.total; s.offs = st->lay.offs;
+  for (int j = 0; j < OCMPS_MAX_L; ++j) s.ptrs.p[j] = nullptr;
+  s.dims = st->dims; s.dims_stride = st->lay.L + 1; s.use_ptrs = 0; s.slot0 = slot0;
+  return s;
+}
+
+// enqueue <bra_z|ket_z> (or <bra|K|ket>) for z < batch; results land in ws->d_out[z]
+int overlaps_async(Workspace* ws, const OvlSide& bra, const Layout& la, const OvlSide& ket, const Layout& lb, int batch,
+                   int withK, cudaStream_t s) {
+  int rc = ensure_overlap_bufs(ws, batch, la.cap, lb.cap);
+  if (rc) return rc;
+  const int L = la.L, D = la.D;
+  const int nE = withK ? 2 : 1;
+  launch_overlap_init(ws->E[0], ws->e_stride, batch, withK, s);
+  int cur = 0;
+  for (int j = 0; j < L; ++j) {
+    launch_overlap_plan(ws->odescs, bra, ket, j, batch, D, withK, ws->E[cur], ws->E[1 - cur], ws->T, ws->e_stride, ws->t_stride, s);
+    launch_zgemm(ws->odescs, batch, nE * la.capb[j], D * lb.capb[j + 1], s);
+    if (withK) launch_overlap_kfix(ws->T, ws->t_stride, ws->odescs, batch, D, la.capb[j] * D * lb.capb[j + 1], s);
+    launch_zgemm(ws->odescs + batch, nE * batch, la.capb[j + 1], lb.capb[j + 1], s);
+    cur = 1 - cur;
+    g_ocmps_launches += 3 + withK;
+  }
+  launch_overlap_final(ws->E[cur], ws->e_stride, batch, withK, ws->d_out, s);
+  g_ocmps_launches += 2;
+  return OCMPS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K|psi> with compression (ITensor exactApplyMPO)
+// ------------------------------------------------------------------------------------------------
+__global__ void copy_bookkeeping_kernel(const int* dims_in, const int* q_in, int qstride_in, int* dims_out, int* q_out,
+                                        int qstride_out, int L, int cap_out, int* status) {
+  for (int b = blockIdx.x; b <= L; b += gridDim.x) {
+    int d = dims_in[b];
+    if (d > cap_out) { if (threadIdx.x == 0) atomicOr(status, OCMPS_ST_CAPACITY); d = cap_out; }
+    if (threadIdx.x == 0) dims_out[b] = d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) q_out[(size_t)b * qstride_out + i] = q_in[(size_t)b * qstride_in + i];
+  }
+}
+
+int apply_K_async(ocmps_stepper* st, Workspace* ws, ocmps_mps* in, ocmps_mps* out, cudaStream_t s) {
+  const int L = st->L, D = st->D;
+  const int cap2 = 2 * st->cap;
+  if ((long long)cap2 * D > NV_MAX) return fail(OCMPS_ERR_INVALID, "apply_K: 2*chi_cap*D exceeds 2048");
+  if (!ws->big) {
+    int rc = alloc_mps(st->ctx, L, D, st->cap, &ws->big, 2);
+    if (rc) return rc;
+    rc = alloc_ws(st->ctx, L, D, cap2, false, &ws->bigws);
+    if (rc) return rc;
+  }
+  ocmps_mps* big = ws->big;
+  Workspace* bw = ws->bigws;
+  const Layout& lb = big->lay;
+  if (L == 1) return fail(OCMPS_ERR_INVALID, "apply_K needs L >= 2");
+  for (int j = 0; j < L; ++j) big->cur[j] = 0;
+  for (int j = 0; j < L; ++j) {
+    launch_applyK_expand(in->site(j), big->site(j), in->dim(j), in->dim(j + 1), in->q(j), in->q(j + 1), big->dim(j), big->dim(j + 1),
+                         big->q(j), big->q(j + 1), D, j, L, lb.capb[j] * D * lb.capb[j + 1], s);
+  }
+  g_ocmps_launches += L;
+  // left-canonicalise the exact product (numerical-rank drops only)
+  TruncParams tpl{MIN_CUT, MAX_M, 1, 1, 0};
+  for (int b = 1; b <= L - 1; ++b) {
+    const int j = b - 1, jn = b;
+    DecompArgs a;
+    a.D = D; a.kind = DK_ORTH_LEFT;
+    a.dimNew = big->dim(b); a.qNew = big->q(b); a.partner = bw->cbuf;
+    a.dimL = big->dim(b - 1); a.dimR = big->dim(b); a.qL = big->q(b - 1); a.qR = big->q(b);
+    a.X = big->site(j); a.iso = big->other(j);
+    a.nb_in = big->site(jn); a.nb_out = big->other(jn); a.dimNb = big->dim(b + 1);
+    tpl.cap = lb.capb[b];
+    run_decomp(bw, a, tpl, lb.capb[b], lb.capb[b - 1], lb.capb[b - 1] * D * lb.capb[b], s);
+    launch_zgemm(bw->db.descs, 1, lb.capb[b], lb.capb[b], s);
+    launch_zgemm(bw->db.descs + 1, 1, lb.capb[b], D * lb.capb[b + 1], s);
+    big->cur[j] ^= 1; big->cur[jn] ^= 1;
+    g_ocmps_launches += 2;
+  }
+  // right-to-left compression with the stepper's Cutoff / Maxm (exactApplyMPO defaults: Cutoff 1e-13)
+  TruncParams tpr{st->has_cutoff ? st->cutoff : 1e-13, st->has_maxm ? st->maxm : MAX_M, 1, st->rel_cutoff, 0};
+  for (int b = L - 1; b >= 1; --b) {
+    const int j = b, jn = b - 1;
+    DecompArgs a;
+    a.D = D; a.kind = DK_ORTH_RIGHT;
+    a.dimNew = big->dim(b); a.qNew = big->q(b); a.partner = bw->cbuf;
+    a.dimL = big->dim(b); a.dimR = big->dim(b + 1); a.qL = big->q(b); a.qR = big->q(b + 1);
+    a.X = big->site(j); a.iso = big->other(j);
+    a.nb_in = big->site(jn); a.nb_out = big->other(jn); a.dimNb = big->dim(b - 1);
+    tpr.cap = std::min(lb.capb[b], out->lay.capb[b]);
+    run_decomp(bw, a, tpr, lb.capb[b], lb.capb[b + 1], lb.capb[b] * D * lb.capb[b + 1], s);
+    launch_zgemm(bw->db.descs, 1, lb.capb[b], lb.capb[b], s);
+    launch_zgemm(bw->db.descs + 1, 1, lb.capb[b - 1] * D, lb.capb[b], s);
+    big->cur[j] ^= 1; big->cur[jn] ^= 1;
+    g_ocmps_launches += 2;
+  }
+  // compact into the chi_cap layout
+  for (int j = 0; j < L; ++j) out->cur[j] = 0;
+  copy_bookkeeping_kernel<<<L + 1, 128, 0, s>>>(big->d_dims, big->d_q, lb.cap, out->d_dims, out->d_q, out->lay.cap, L, out->lay.cap,
+                                               st->ctx->d_status);
+  launch_pack_copy(big->ptrs(), out->arena[0], out->lay.offs, out->d_dims, L, D, out->lay.max_site_elems, s);
+  g_ocmps_launches += 2;
+  out->llim = 0; out->rlim = 2;
+  return OCMPS_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* ocmps_last_error(void) { return g_err.c_str(); }
+int ocmps_version(void) { return 100; }
+long long ocmps_launch_count(void) { return g_ocmps_launches; }
+
+int ocmps_ctx_create(int device, ocmps_ctx** out) {
+  if (!out) return fail(OCMPS_ERR_INVALID, "null out");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return fail(OCMPS_ERR_CUDA, "no CUDA device available (libocmps has no CPU fallback)");
+  if (device < 0 || device >= n) return fail(OCMPS_ERR_INVALID, "device index out of range");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(OCMPS_ERR_CUDA, "libocmps is built for sm_100a (Blackwell) only");
+  ocmps_ctx* c = new ocmps_ctx();
+  c->dev = device;
+  CK(cudaMalloc(&c->d_status, sizeof(int)));
+  CK(cudaMemset(c->d_status, 0, sizeof(int)));
+  CK(cudaStreamCreateWithFlags(&c->stream0, cudaStreamNonBlocking));
+  *out = c;
+  return OCMPS_OK;
+}
+
+int ocmps_ctx_destroy(ocmps_ctx* ctx) {
+  if (!ctx) return OCMPS_OK;
+  cudaSetDevice(ctx->dev);
+  cudaDeviceSynchronize();
+  for (Workspace* w : ctx->pool) free_ws(w);
+  cudaFree(ctx->d_status);
+  cudaStreamDestroy(ctx->stream0);
+  delete ctx;
+  return OCMPS_OK;
+}
+
+int ocmps_ctx_synchronize(ocmps_ctx* ctx) {
+  CK(cudaSetDevice(ctx->dev));
+  CK(cudaDeviceSynchronize());
+  return check_status(ctx);
+}
+
+// ---- MPS ----
+int ocmps_mps_create(ocmps_ctx* ctx, int L, int D, int chi_cap, ocmps_mps** out) {
+  if (!ctx || !out) return fail(OCMPS_ERR_INVALID, "null argument");
+  return alloc_mps(ctx, L, D, chi_cap, out);
+}
+int ocmps_mps_destroy(ocmps_mps* mps) {
+  if (mps) { cudaSetDevice(mps->ctx->dev); cudaDeviceSynchronize(); free_mps(mps); }
+  return OCMPS_OK;
+}
+
+int ocmps_mps_upload(ocmps_mps* m, const int* bond_dims, const int* charges, const double* tensors, int llim, int rlim) {
+  if (!m || !bond_dims || !charges || !tensors) return fail(OCMPS_ERR_INVALID, "null argument");
+  const Layout& lay = m->lay;
+  CK(cudaSetDevice(m->ctx->dev));
+  CK(cudaDeviceSynchronize());
+  for (int b = 0; b <= lay.L; ++b)
+    if (bond_dims[b] < 1 || bond_dims[b] > lay.capb[b])
+      return fail(OCMPS_ERR_CAPACITY, "upload: bond dimension " + std::to_string(bond_dims[b]) + " at bond " + std::to_string(b) +
+                                          " exceeds capacity " + std::to_string(lay.capb[b]));
+  if (bond_dims[0] != 1 || bond_dims[lay.L] != 1) return fail(OCMPS_ERR_INVALID, "upload: boundary bonds must have dimension 1");
+  size_t off = 0, qoff = 0;
+  for (int j = 0; j < lay.L; ++j) {
+    m->cur[j] = 0;
+    size_t n = (size_t)bond_dims[j] * lay.D * bond_dims[j + 1];
+    CK(cudaMemcpy(m->site(j), tensors + 2 * off, sizeof(cplx) * n, cudaMemcpyHostToDevice));
+    off += n;
+  }
+  for (int b = 0; b <= lay.L; ++b) {
+    for (int i = 0; i < bond_dims[b]; ++i)
+      if (charges[qoff + i] < 0 || charges[qoff + i] >= OCMPS_MAX_Q) return fail(OCMPS_ERR_INVALID, "upload: charge outside [0,256)");
+    CK(cudaMemcpy(m->q(b), charges + qoff, sizeof(int) * bond_dims[b], cudaMemcpyHostToDevice));
+    qoff += bond_dims[b];
+  }
+  CK(cudaMemcpy(m->d_dims, bond_dims, sizeof(int) * (lay.L + 1), cudaMemcpyHostToDevice));
+  m->llim = llim; m->rlim = rlim;
+  return OCMPS_OK;
+}
+
+int ocmps_mps_bond_dims(ocmps_mps* m, int* bond_dims) {
+  if (!m || !bond_dims) return fail(OCMPS_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(m->ctx->dev));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(bond_dims, m->d_dims, sizeof(int) * (m->lay.L + 1), cudaMemcpyDeviceToHost));
+  return check_status(m->ctx);
+}
+
+int ocmps_mps_sizes(ocmps_mps* m, long long* n_elems, long long* n_charges) {
+  std::vector<int> d(m->lay.L + 1);
+  int rc = ocmps_mps_bond_dims(m, d.data());
+  if (rc) return rc;
+  long long ne = 0, nq = 0;
+  for (int j = 0; j < m->lay.L; ++j) ne += (long long)d[j] * m->lay.D * d[j + 1];
+  for (int b = 0; b <= m->lay.L; ++b) nq += d[b];
+  if (n_elems) *n_elems = ne;
+  if (n_charges) *n_charges = nq;
+  return OCMPS_OK;
+}
+
+int ocmps_mps_download(ocmps_mps* m, int* bond_dims, int* charges, double* tensors, int* llim, int* rlim) {
+  if (!m || !bond_dims) return fail(OCMPS_ERR_INVALID, "null argument");
+  int rc = ocmps_mps_bond_dims(m, bond_dims);
+  if (rc) return rc;
+  const Layout& lay = m->lay;
+  size_t off = 0, qoff = 0;
+  for (int j = 0; j < lay.L; ++j) {
+    size_t n = (size_t)bond_dims[j] * lay.D * bond_dims[j + 1];
+    if (tensors) CK(cudaMemcpy(tensors + 2 * off, m->site(j), sizeof(cplx) * n, cudaMemcpyDeviceToHost));
+    off += n;
+  }
+  for (int b = 0; b <= lay.L; ++b) {
+    if (charges) CK(cudaMemcpy(charges + qoff, m->q(b), sizeof(int) * bond_dims[b], cudaMemcpyDeviceToHost));
+    qoff += bond_dims[b];
+  }
+  if (llim) *llim = m->llim;
+  if (rlim) *rlim = m->rlim;
+  return OCMPS_OK;
+}
+
+int ocmps_mps_copy(ocmps_mps* dst, ocmps_mps* src) {
+  if (!dst || !src) return fail(OCMPS_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(src->ctx->dev));
+  CK(cudaDeviceSynchronize());
+  int rc = copy_mps_async(dst, src, src->ctx->stream0);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(src->ctx->stream0));
+  return OCMPS_OK;
+}
+
+int ocmps_mps_norm(ocmps_mps* m, double* out) {
+  if (!m || !out) return fail(OCMPS_ERR_INVALID, "null argument");
+  if (m->llim + 2 != m->rlim) return fail(OCMPS_ERR_INVALID, "norm: MPS has no single orthogonality centre");
+  CK(cudaSetDevice(m->ctx->dev));
+  Workspace* ws = nullptr;
+  int rc = get_ws(m->ctx, m->lay.L, m->lay.D, m->lay.cap, 0, &ws);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  const int j = m->llim;   // 0-based centre
+  launch_norm_only(m->site(j), m->dim(j), m->dim(j + 1), m->lay.D, ws->db.partial, ws->d_norm, 0, ws->stream);
+  g_ocmps_launches += 2;
+  CK(cudaMemcpyAsync(out, ws->d_norm, sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
+  CK(cudaStreamSynchronize(ws->stream));
+  return OCMPS_OK;
+}
+
+static int overlap_impl(ocmps_mps* a, ocmps_mps* b, double* re_im, int withK) {
+  if (!a || !b || !re_im) return fail(OCMPS_ERR_INVALID, "null argument");
+  if (a->lay.L != b->lay.L || a->lay.D != b->lay.D) return fail(OCMPS_ERR_INVALID, "overlap: shape mismatch");
+  CK(cudaSetDevice(a->ctx->dev));
+  Workspace* ws = nullptr;
+  int rc = get_ws(a->ctx, a->lay.L, a->lay.D, a->lay.cap, 0, &ws);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  rc = overlaps_async(ws, side_of_mps(a), a->lay, side_of_mps(b), b->lay, 1, withK, ws->stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(re_im, ws->d_out, sizeof(cplx), cudaMemcpyDeviceToHost, ws->stream));
+  CK(cudaStreamSynchronize(ws->stream));
+  return OCMPS_OK;
+}
+int ocmps_overlap(ocmps_mps* a, ocmps_mps* b, double* re_im) { return overlap_impl(a, b, re_im, 0); }
+int ocmps_overlap_K(ocmps_mps* a, ocmps_mps* b, double* re_im) { return overlap_impl(a, b, re_im, 1); }
+
+// ---- stepper ----
+int ocmps_stepper_set_tstep(ocmps_stepper* st, double tstep) {
+  if (!st) return fail(OCMPS_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(st->ctx->dev));
+  CK(cudaDeviceSynchronize());
+  st->tstep = tstep;
+  const int n = st->D * st->D;
+  for (int dir = 0; dir < 2; ++dir) {
+    st->h_G[dir] = bond_gate(st->D, st->J, dir == 0 ? tstep : -tstep);
+    if (!st->d_G[dir]) CK(cudaMalloc(&st->d_G[dir], sizeof(cplx) * n * n));
+    CK(cudaMemcpy(st->d_G[dir], st->h_G[dir].data(), sizeof(cplx) * n * n, cudaMemcpyHostToDevice));
+  }
+  return OCMPS_OK;
+}
+
+int ocmps_stepper_create(ocmps_ctx* ctx, int L, int D, double J, double tstep, double cutoff, int maxm, int chi_cap, int rel_cutoff,
+                         ocmps_stepper** out) {
+  if (!ctx || !out) return fail(OCMPS_ERR_INVALID, "null argument");
+  if (L < 2 || L > OCMPS_MAX_L) return fail(OCMPS_ERR_INVALID, "L out of range [2,64]");
+  if (D < 2 || D > OCMPS_MAX_D) return fail(OCMPS_ERR_INVALID, "D out of range [2,8]");
+  if (chi_cap < 1 || (long long)chi_cap * D > NV_MAX) return fail(OCMPS_ERR_INVALID, "chi_cap*D exceeds 2048");
+  ocmps_stepper* st = new ocmps_stepper();
+  st->ctx = ctx; st->L = L; st->D = D; st->J = J; st->cap = chi_cap;
+  st->has_cutoff = cutoff >= 0.0; st->cutoff = st->has_cutoff ? cutoff : MIN_CUT;
+  st->has_maxm = maxm > 0; st->maxm = st->has_maxm ? maxm : MAX_M;
+  st->rel_cutoff = rel_cutoff ? 1 : 0;
+  st->ops = build_schedule(L);
+  int rc = ocmps_stepper_set_tstep(st, tstep);
+  if (rc) { delete st; return rc; }
+  *out = st;
+  return OCMPS_OK;
+}
+
+int ocmps_stepper_destroy(ocmps_stepper* st) {
+  if (!st) return OCMPS_OK;
+  cudaSetDevice(st->ctx->dev);
+  cudaDeviceSynchronize();
+  cudaFree(st->d_G[0]); cudaFree(st->d_G[1]);
+  delete st;
+  return OCMPS_OK;
+}
+
+double ocmps_stepper_get_tstep(ocmps_stepper* st) { return st ? st->tstep : 0.0; }
+
+int ocmps_stepper_schedule(ocmps_stepper* st, int* quads, int cap) {
+  if (!st) return fail(OCMPS_ERR_INVALID, "null argument");
+  int n = (int)st->ops.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    quads[4 * i] = st->ops[i].kind; quads[4 * i + 1] = st->ops[i].a; quads[4 * i + 2] = st->ops[i].b; quads[4 * i + 3] = st->ops[i].c;
+  }
+  return n;
+}
+
+int ocmps_stepper_gate(ocmps_stepper* st, int forward, double* out) {
+  if (!st || !out) return fail(OCMPS_ERR_INVALID, "null argument");
+  const std::vector<zc>& g = st->h_G[forward ? 0 : 1];
+  memcpy(out, g.data(), sizeof(zc) * g.size());
+  return OCMPS_OK;
+}
+
+static int check_shapes(ocmps_stepper* st, const Layout& lay, const char* what) {
+  if (lay.L != st->L || lay.D != st->D || lay.cap != st->cap)
+    return fail(OCMPS_ERR_INVALID, std::string(what) + ": MPS/store shape (L, D, chi_cap) differs from the stepper's");
+  return OCMPS_OK;
+}
+
+int ocmps_step(ocmps_stepper* st, ocmps_mps* psi, double from, double to, int forward) {
+  if (!st || !psi) return fail(OCMPS_ERR_INVALID, "null argument");
+  int rc = check_shapes(st, psi->lay, "step");
+  if (rc) return rc;
+  if (psi->llim != 0 || psi->rlim != 2) return fail(OCMPS_ERR_INVALID, "step: orthogonality centre must be at site 1");
+  CK(cudaSetDevice(st->ctx->dev));
+  Workspace* ws = nullptr;
+  rc = get_ws(st->ctx, st->L, st->D, st->cap, 0, &ws);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  run_step(st, psi, ws, from, to, forward != 0, ws->stream);
+  CK(cudaStreamSynchronize(ws->stream));
+  CK(cudaGetLastError());
+  return check_status(st->ctx);
+}
+
+// development aid: run ops [op_begin, op_end) of one step (not part of include/ocmps.h)
+int ocmps_debug_run_ops(ocmps_stepper* st, ocmps_mps* psi, double from, double to, int forward, int op_begin, int op_end) {
+  CK(cudaSetDevice(st->ctx->dev));
+  Workspace* ws = nullptr;
+  int rc = get_ws(st->ctx, st->L, st->D, st->cap, 0, &ws);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  run_step(st, psi, ws, from, to, forward != 0, ws->stream, op_begin, op_end);
+  CK(cudaStreamSynchronize(ws->stream));
+  CK(cudaGetLastError());
+  return check_status(st->ctx);
+}
+
+int ocmps_apply_K(ocmps_stepper* st, ocmps_mps* in, ocmps_mps* out) {
+  if (!st || !in || !out) return fail(OCMPS_ERR_INVALID, "null argument");
+  int rc = check_shapes(st, in->lay, "apply_K");
+  if (rc) return rc;
+  rc = check_shapes(st, out->lay, "apply_K");
+  if (rc) return rc;
+  CK(cudaSetDevice(st->ctx->dev));
+  Workspace* ws = nullptr;
+  rc = get_ws(st->ctx, st->L, st->D, st->cap, 0, &ws);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  rc = apply_K_async(st, ws, in, out, ws->stream);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ws->stream));
+  CK(cudaGetLastError());
+  return check_status(st->ctx);
+}
+
+// ---- stores ----
+int ocmps_store_create(ocmps_ctx* ctx, int L, int D, int chi_cap, int nslots, ocmps_store** out) {
+  if (!ctx || !out || nslots < 1) return fail(OCMPS_ERR_INVALID, "bad argument");
+  if (L < 1 || L > OCMPS_MAX_L || D < 2 || D > OCMPS_MAX_D || chi_cap < 1) return fail(OCMPS_ERR_INVALID, "bad shape");
+  ocmps_store* s = new ocmps_store();
+  s->ctx = ctx; s->nslots = nslots;
+  s->lay.init(L, D, chi_cap);
+  CK(cudaSetDevice(ctx->dev));
+  CK(cudaMalloc(&s->data, sizeof(cplx) * (size_t)s->lay.total * nslots));
+  CK(cudaMalloc(&s->dims, sizeof(int) * (size_t)(L + 1) * nslots));
+  CK(cudaMalloc(&s->q, sizeof(int) * (size_t)(L + 1) * chi_cap * nslots));
+  CK(cudaMemset(s->dims, 0, sizeof(int) * (size_t)(L + 1) * nslots));
+  *out = s;
+  return OCMPS_OK;
+}
+int ocmps_store_destroy(ocmps_store* s) {
+  if (!s) return OCMPS_OK;
+  cudaSetDevice(s->ctx->dev);
+  cudaDeviceSynchronize();
+  cudaFree(s->data); cudaFree(s->dims); cudaFree(s->q);
+  delete s;
+  return OCMPS_OK;
+}
+int ocmps_store_get(ocmps_store* store, int slot, ocmps_mps* out) {
+  if (!store || !out) return fail(OCMPS_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(store->ctx->dev));
+  CK(cudaDeviceSynchronize());
+  int rc = store_get_async(store, slot, out, store->ctx->stream0);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(store->ctx->stream0));
+  return OCMPS_OK;
+}
+int ocmps_store_put(ocmps_store* store, int slot, ocmps_mps* in) {
+  if (!store || !in) return fail(OCMPS_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(store->ctx->dev));
+  CK(cudaDeviceSynchronize());
+  int rc = store_put_async(store, slot, in, store->ctx->stream0);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(store->ctx->stream0));
+  return OCMPS_OK;
+}
+int ocmps_store_bond_dims(ocmps_store* store, int* out) {
+  if (!store || !out) return fail(OCMPS_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(store->ctx->dev));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, store->dims, sizeof(int) * (size_t)(store->lay.L + 1) * store->nslots, cudaMemcpyDeviceToHost));
+  return OCMPS_OK;
+}
+
+// ---- sweeps ----
+static int sweep_enqueue_init(ocmps_stepper* st, Workspace* ws, ocmps_mps* start, ocmps_store* store, int slot) {
+  int rc = copy_mps_async(ws->work, start, ws->stream);
+  if (rc) return rc;
+  ws->work->llim = 0; ws->work->rlim = 2;
+  if (store) return store_put_async(store, slot, ws->work, ws->stream);
+  return OCMPS_OK;
+}
+
+static int sweep_args_ok(ocmps_stepper* st, ocmps_mps* start, const double* u, int Nt, ocmps_store* store) {
+  if (!st || !start || !u || Nt < 2) return fail(OCMPS_ERR_INVALID, "bad argument");
+  int rc = check_shapes(st, start->lay, "sweep");
+  if (rc) return rc;
+  if (start->llim != 0 || start->rlim != 2) return fail(OCMPS_ERR_INVALID, "sweep: orthogonality centre must be at site 1");
+  if (store) {
+    rc = check_shapes(st, store->lay, "sweep");
+    if (rc) return rc;
+    if (store->nslots < Nt) return fail(OCMPS_ERR_INVALID, "sweep: store has fewer slots than Nt");
+  }
+  return OCMPS_OK;
+}
+
+int ocmps_forward_sweep(ocmps_stepper* st, ocmps_mps* psi_init, const double* u, int Nt, ocmps_store* store) {
+  int rc = sweep_args_ok(st, psi_init, u, Nt, store);
+  if (rc) return rc;
+  if (!store) return fail(OCMPS_ERR_INVALID, "null store");
+  CK(cudaSetDevice(st->ctx->dev));
+  Workspace* ws = nullptr;
+  rc = get_ws(st->ctx, st->L, st->D, st->cap, 0, &ws);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  rc = sweep_enqueue_init(st, ws, psi_init, store, 0);
+  if (rc) return rc;
+  for (int i = 0; i < Nt - 1; ++i) {
+    run_step(st, ws->work, ws, u[i], u[i + 1], true, ws->stream);
+    rc = store_put_async(store, i + 1, ws->work, ws->stream);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(ws->stream));
+  CK(cudaGetLastError());
+  return check_status(st->ctx);
+}
+
+int ocmps_backward_sweep(ocmps_stepper* st, ocmps_mps* psi_target, const double* u, int Nt, ocmps_store* store) {
+  int rc = sweep_args_ok(st, psi_target, u, Nt, store);
+  if (rc) return rc;
+  if (!store) return fail(OCMPS_ERR_INVALID, "null store");
+  CK(cudaSetDevice(st->ctx->dev));
+  Workspace* ws = nullptr;
+  rc = get_ws(st->ctx, st->L, st->D, st->cap, 1, &ws);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  rc = sweep_enqueue_init(st, ws, psi_target, store, Nt - 1);
+  if (rc) return rc;
+  for (int i = Nt - 1; i > 0; --i) {
+    run_step(st, ws->work, ws, u[i], u[i - 1], false, ws->stream);
+    rc = store_put_async(store, i - 1, ws->work, ws->stream);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(ws->stream));
+  CK(cudaGetLastError());
+  return check_status(st->ctx);
+}
+
+int ocmps_sweep_pair(ocmps_stepper* st, ocmps_mps* psi_init, ocmps_mps* psi_target, const double* u, int Nt, ocmps_store* psi_store,
+                     ocmps_store* xi_store) {
+  int rc = sweep_args_ok(st, psi_init, u, Nt, psi_store);
+  if (rc) return rc;
+  rc = sweep_args_ok(st, psi_target, u, Nt, xi_store);
+  if (rc) return rc;
+  if (!psi_store || !xi_store) return fail(OCMPS_ERR_INVALID, "null store");
+  CK(cudaSetDevice(st->ctx->dev));
+  Workspace *wa = nullptr, *wb = nullptr;
+  rc = get_ws(st->ctx, st->L, st->D, st->cap, 0, &wa);
+  if (rc) return rc;
+  rc = get_ws(st->ctx, st->L, st->D, st->cap, 1, &wb);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  rc = sweep_enqueue_init(st, wa, psi_init, psi_store, 0);
+  if (rc) return rc;
+  rc = sweep_enqueue_init(st, wb, psi_target, xi_store, Nt - 1);
+  if (rc) return rc;
+  for (int k = 0; k < Nt - 1; ++k) {      // interleave the two chains so both streams stay fed
+    run_step(st, wa->work, wa, u[k], u[k + 1], true, wa->stream);
+    rc = store_put_async(psi_store, k + 1, wa->work, wa->stream);
+    if (rc) return rc;
+    const int i = Nt - 1 - k;
+    run_step(st, wb->work, wb, u[i], u[i - 1], false, wb->stream);
+    rc = store_put_async(xi_store, i - 1, wb->work, wb->stream);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(wa->stream));
+  CK(cudaStreamSynchronize(wb->stream));
+  CK(cudaGetLastError());
+  return check_status(st->ctx);
+}
+
+int ocmps_backward_sweep_divT(ocmps_stepper* st, ocmps_mps* psi_target, const double* u, int Nt, ocmps_store* psi_store,
+                              double* divT) {
+  int rc = sweep_args_ok(st, psi_target, u, Nt, psi_store);
+  if (rc) return rc;
+  if (!psi_store || !divT) return fail(OCMPS_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(st->ctx->dev));
+  Workspace* ws = nullptr;
+  rc = get_ws(st->ctx, st->L, st->D, st->cap, 1, &ws);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  rc = sweep_enqueue_init(st, ws, psi_target, nullptr, 0);
+  if (rc) return rc;
+  cplx* d_div = nullptr;
+  CK(cudaMalloc(&d_div, sizeof(cplx) * Nt));
+  for (int i = Nt - 1; i >= 0; --i) {
+    rc = overlaps_async(ws, side_of_mps(ws->work), ws->work->lay, side_of_store(psi_store, i), psi_store->lay, 1, 1, ws->stream);
+    if (rc) { cudaFree(d_div); return rc; }
+    CK(cudaMemcpyAsync(d_div + i, ws->d_out, sizeof(cplx), cudaMemcpyDeviceToDevice, ws->stream));
+    if (i > 0) run_step(st, ws->work, ws, u[i], u[i - 1], false, ws->stream);
+  }
+  CK(cudaMemcpyAsync(divT, d_div, sizeof(cplx) * Nt, cudaMemcpyDeviceToHost, ws->stream));
+  CK(cudaStreamSynchronize(ws->stream));
+  cudaFree(d_div);
+  CK(cudaGetLastError());
+  return check_status(st->ctx);
+}
+
+static int store_overlaps_impl(ocmps_store* bra_store, ocmps_mps* bra, ocmps_store* ket, int Nt, int withK, double* out) {
+  if (!ket || !out || Nt < 1 || Nt > ket->nslots) return fail(OCMPS_ERR_INVALID, "bad argument");
+  ocmps_ctx* ctx = ket->ctx;
+  CK(cudaSetDevice(ctx->dev));
+  Workspace* ws = nullptr;
+  int rc = get_ws(ctx, ket->lay.L, ket->lay.D, ket->lay.cap, 0, &ws);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  const int chunk = 64;
+  for (int z0 = 0; z0 < Nt; z0 += chunk) {
+    const int nb = std::min(chunk, Nt - z0);
+    OvlSide sb = bra ? side_of_mps(bra) : side_of_store(bra_store, z0);
+    const Layout& la = bra ? bra->lay : bra_store->lay;
+    rc = overlaps_async(ws, sb, la, side_of_store(ket, z0), ket->lay, nb, withK, ws->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out + 2 * z0, ws->d_out, sizeof(cplx) * nb, cudaMemcpyDeviceToHost, ws->stream));
+    CK(cudaStreamSynchronize(ws->stream));
+  }
+  CK(cudaGetLastError());
+  return OCMPS_OK;
+}
+
+int ocmps_store_overlaps(ocmps_store* store, ocmps_mps* bra, int Nt, double* out) {
+  if (!bra) return fail(OCMPS_ERR_INVALID, "null bra");
+  return store_overlaps_impl(nullptr, bra, store, Nt, 0, out);
+}
+int ocmps_store_divT(ocmps_store* xi_store, ocmps_store* psi_store, int Nt, double* out) {
+  if (!xi_store) return fail(OCMPS_ERR_INVALID, "null store");
+  return store_overlaps_impl(xi_store, nullptr, psi_store, Nt, 1, out);
+}
+
+int ocmps_store_apply_K(ocmps_stepper* st, ocmps_store* in, int Nt, ocmps_store* out) {
+  if (!st || !in || !out || Nt < 1 || Nt > in->nslots || Nt > out->nslots) return fail(OCMPS_ERR_INVALID, "bad argument");
+  int rc = check_shapes(st, in->lay, "store_apply_K");
+  if (rc) return rc;
+  rc = check_shapes(st, out->lay, "store_apply_K");
+  if (rc) return rc;
+  CK(cudaSetDevice(st->ctx->dev));
+  const int nch = std::min(Nt, 8);
+  std::vector<Workspace*> wss(nch);
+  std::vector<ocmps_mps*> tmp(nch, nullptr);
+  for (int c = 0; c < nch; ++c) {
+    rc = get_ws(st->ctx, st->L, st->D, st->cap, c, &wss[c]);
+    if (rc) return rc;
+    rc = alloc_mps(st->ctx, st->L, st->D, st->cap, &tmp[c]);
+    if (rc) return rc;
+  }
+  CK(cudaDeviceSynchronize());
+  for (int i = 0; i < Nt; ++i) {
+    Workspace* ws = wss[i % nch];
+    rc = store_get_async(in, i, ws->work, ws->stream);
+    if (!rc) rc = apply_K_async(st, ws, ws->work, tmp[i % nch], ws->stream);
+    if (!rc) rc = store_put_async(out, i, tmp[i % nch], ws->stream);
+    if (rc) break;
+  }
+  CK(cudaDeviceSynchronize());
+  for (int c = 0; c < nch; ++c) free_mps(tmp[c]);
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  return check_status(st->ctx);
+}
+
+int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* xiH_store, const double* u, int Nt, const int* rows,
+                       int nrows, int nchains, double* ovl, double* norms) {
+  if (!st || !psi_store || !xiH_store || !u || !rows || !ovl || !norms || Nt < 3) return fail(OCMPS_ERR_INVALID, "bad argument");
+  int rc = check_shapes(st, psi_store->lay, "hessian_rows");
+  if (rc) return rc;
+  rc = check_shapes(st, xiH_store->lay, "hessian_rows");
+  if (rc) return rc;
+  if (nchains < 1) nchains = 1;
+  nchains = std::min(nchains, std::max(nrows, 1));
+  CK(cudaSetDevice(st->ctx->dev));
+  std::vector<Workspace*> wss(nchains);
+  std::vector<ocmps_mps*> psiH(nchains, nullptr);
+  for (int c = 0; c < nchains; ++c) {
+    rc = get_ws(st->ctx, st->L, st->D, st->cap, c, &wss[c]);
+    if (rc) return rc;
+    rc = alloc_mps(st->ctx, st->L, st->D, st->cap, &psiH[c]);
+    if (rc) return rc;
+  }
+  cplx* d_ovl = nullptr;
+  double* d_norms = nullptr;
+  CK(cudaMalloc(&d_ovl, sizeof(cplx) * (size_t)Nt * Nt));
+  CK(cudaMalloc(&d_norms, sizeof(double) * Nt));
+  CK(cudaMemset(d_ovl, 0, sizeof(cplx) * (size_t)Nt * Nt));
+  CK(cudaMemset(d_norms, 0, sizeof(double) * Nt));
+  CK(cudaDeviceSynchronize());
+  // longest rows first, dealt round-robin to the chains; chains advance in lock step so every stream stays fed
+  std::vector<int> order(rows, rows + nrows);
+  std::sort(order.begin(), order.end());
+  struct ChainState { int row = -1; int j = 0; size_t next = 0; };
+  std::vector<std::vector<int>> mine(nchains);
+  for (int i = 0; i < nrows; ++i) mine[i % nchains].push_back(order[i]);
+  std::vector<ChainState> cs(nchains);
+  bool busy = true;
+  rc = OCMPS_OK;
+  while (busy && !rc) {
+    busy = false;
+    for (int c = 0; c < nchains && !rc; ++c) {
+      ChainState& S = cs[c];
+      Workspace* ws = wss[c];
+      if (S.row < 0) {
+        if (S.next >= mine[c].size()) continue;
+        S.row = mine[c][S.next++];
+        if (S.row < 1 || S.row > Nt - 2) { rc = fail(OCMPS_ERR_INVALID, "hessian row out of range [1, Nt-2]"); break; }
+        // psiH = K|psi_row>, its norm, diagonal overlap (src/OptimalControl.cpp:256-264)
+        rc = store_get_async(psi_store, S.row, ws->work, ws->stream);
+        if (!rc) rc = apply_K_async(st, ws, ws->work, psiH[c], ws->stream);
+        if (rc) break;
+        launch_norm_only(psiH[c]->site(0), psiH[c]->dim(0), psiH[c]->dim(1), st->D, ws->db.partial, d_norms + S.row, 0, ws->stream);
+        g_ocmps_launches += 2;
+        rc = overlaps_async(ws, side_of_store(xiH_store, S.row), xiH_store->lay, side_of_mps(psiH[c]), psiH[c]->lay, 1, 0, ws->stream);
+        if (rc) break;
+        CK(cudaMemcpyAsync(d_ovl + (size_t)S.row * Nt + S.row, ws->d_out, sizeof(cplx), cudaMemcpyDeviceToDevice, ws->stream));
+        S.j = S.row + 1;
+        busy = true;
+      } else {
+        if (S.j >= Nt - 1) { S.row = -1; busy = true; continue; }
+        // one step forward and the overlap with xiH_j (:267-277)
+        run_step(st, psiH[c], ws, u[S.j - 1], u[S.j], true, ws->stream);
+        rc = overlaps_async(ws, side_of_store(xiH_store, S.j), xiH_store->lay, side_of_mps(psiH[c]), psiH[c]->lay, 1, 0, ws->stream);
+        if (rc) break;
+        CK(cudaMemcpyAsync(d_ovl + (size_t)S.row * Nt + S.j, ws->d_out, sizeof(cplx), cudaMemcpyDeviceToDevice, ws->stream));
+        ++S.j;
+        busy = true;
+      }
+    }
+  }
+  cudaDeviceSynchronize();
+  if (!rc) {
+    cudaMemcpy(ovl, d_ovl, sizeof(cplx) * (size_t)Nt * Nt, cudaMemcpyDeviceToHost);
+    cudaMemcpy(norms, d_norms, sizeof(double) * Nt, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d_ovl); cudaFree(d_norms);
+  for (int c = 0; c < nchains; ++c) free_mps(psiH[c]);
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  return check_status(st->ctx);
+}
+
+}  // extern "C"
