@@ -1,21 +1,30 @@
-// Truncated decompositions of the engine: charge-blocked one-sided Jacobi SVD in shared memory.
+// Truncated decompositions of the engine: charge-blocked, QR-preconditioned one-sided Jacobi SVD in
+// shared memory.
 //
 // The reference truncates with ITensor's denmatDecomp (eigen-decomposition of the two-site reduced
 // density matrix, i.e. the Gram matrix theta.theta^H) per particle-number block, followed by a
 // global sort of all eigenvalues and the Cutoff/Maxm rule, and moves the
 // orthogonality centre with block SVDs (A.4).  The eigenvalues of the Gram matrix are the squared
-// singular values of theta, and its eigenvectors are the singular vectors, so here each charge block
-// X_q is orthogonalised directly with Hestenes' one-sided Jacobi: pairs of vectors are rotated until
-// all Gram entries <y_p|y_q> vanish; the Gram diagonal (squared norms) is the spectrum the truncation
-// rule sees.  One CTA per block, the block lives in shared memory, one warp per vector pair, dot
-// products by warp shuffles.
+// singular values of theta and its eigenvectors are the singular vectors, so each charge block
+// M (len x nv, columns = the vectors to orthogonalise) is decomposed as M = U D Z directly:
+//   1. Householder QR with column pivoting, M P = Q R, in shared memory (rank revealing; k <= min(len, nv));
+//   2. Hestenes one-sided Jacobi on the k rows of R (Drmac-Veselic preconditioning: 6-7 sweeps instead of
+//      the ~20 plain cyclic Jacobi needs on these strongly graded spectra): pairs of rows are rotated
+//      until every Gram entry <r_p|r_q> vanishes; one half-warp per pair, dot products by shuffles;
+//      the Gram diagonal (squared norms) is the spectrum the truncation rule sees;
+//   3. after the global truncation, only the kept left vectors are formed, u_j = M z_j^H / |M z_j^H|.
+// One CTA per block.
 #include "ocmps_internal.h"
+
+__device__ unsigned long long g_jac_dbg[8];   // [0] sum of sweeps, [1] blocks, [2] max sweeps, [3] sweeps of blocks with nv>=64, [4] such blocks
 
 namespace {
 
-constexpr int JAC_THREADS = 512;
+constexpr int JAC_THREADS = 1024;
+constexpr int JAC_NV_SMEM = 512;          // cached norms in shared memory for blocks with at most this many vectors
 constexpr int JAC_MAX_SWEEPS = 60;
 constexpr double JAC_TOL2 = 1e-28;        // rotate while |<p|q>|^2 > tol^2 <p|p><q|q>, tol = 1e-14
+constexpr double DEFLATE_REL = 1e-30;     // vectors below this fraction of the block's weight are numerically zero
 constexpr int NV_MAX = 2048;              // max number of vectors in one decomposition
 
 // ------------------------------------------------------------------------------------------------
@@ -43,27 +52,39 @@ __device__ __forceinline__ int col_charge(const DecompArgs& a, int j, int chiR) 
 // comp_blk / comp_rank live behind comp_idx in the same allocation (see engine: 3 * NV_MAX ints)
 __global__ void __launch_bounds__(OCMPS_MAX_Q) decomp_setup_kernel(DecompArgs a, DecompBuffers b) {
   __shared__ int cnt_v[OCMPS_MAX_Q], cnt_c[OCMPS_MAX_Q], off_v[OCMPS_MAX_Q], off_c[OCMPS_MAX_Q], blk_of_q[OCMPS_MAX_Q];
+  __shared__ short s_rq[NV_MAX], s_cq[NV_MAX];      // charges of rows / columns (-1: outside [0, MAX_Q))
+  __shared__ int s_bad;
   const int chiL = *a.dimL, chiR = *a.dimR;
   const Geometry g = geometry(a, chiL, chiR);
   const int q = threadIdx.x;
-  const int nvec = g.mode == 0 ? g.m : g.n;
   const int ncomp = g.mode == 0 ? g.n : g.m;
   int* comp_blk = b.comp_idx + NV_MAX;
   int* comp_rank = b.comp_idx + 2 * NV_MAX;
-
-  int cv = 0, cc = 0, bad = 0;
-  for (int i = 0; i < g.n; ++i) {
+  int* vec_blk = b.vec_idx + NV_MAX;
+  int* vec_rank = b.vec_idx + 2 * NV_MAX;
+  if (q == 0) s_bad = 0;
+  __syncthreads();
+  for (int i = q; i < g.n; i += blockDim.x) {
     int c = row_charge(a, i);
-    if (c >= OCMPS_MAX_Q) bad = 1;
-    if (c == q) { if (g.mode == 0) ++cc; else ++cv; }
+    if (c >= OCMPS_MAX_Q) { s_bad = 1; c = -1; }
+    s_rq[i] = (short)(c < 0 ? -1 : c);
   }
-  for (int j = 0; j < g.m; ++j) {
+  for (int j = q; j < g.m; j += blockDim.x) {
     int c = col_charge(a, j, chiR);
-    if (c >= OCMPS_MAX_Q) bad = 1;
-    if (c == q) { if (g.mode == 0) ++cv; else ++cc; }
+    if (c >= OCMPS_MAX_Q) { s_bad = 1; c = -1; }
+    s_cq[j] = (short)(c < 0 ? -1 : c);
   }
+  for (int i = q; i < ncomp; i += blockDim.x) { comp_blk[i] = -1; comp_rank[i] = 0; }
+  for (int i = q; i < (g.mode == 0 ? g.m : g.n); i += blockDim.x) { vec_blk[i] = -1; vec_rank[i] = 0; }
+  __syncthreads();
+  const short* vq = g.mode == 0 ? s_cq : s_rq;      // vectors: columns (mode 0) or rows (mode 1)
+  const short* cq = g.mode == 0 ? s_rq : s_cq;
+  const int nvec = g.mode == 0 ? g.m : g.n;
+  int cv = 0, cc = 0;
+  for (int i = 0; i < nvec; ++i) cv += (vq[i] == q);
+  for (int i = 0; i < ncomp; ++i) cc += (cq[i] == q);
   cnt_v[q] = cv; cnt_c[q] = cc;
-  if (bad && q == 0) atomicOr(b.status, OCMPS_ST_CHARGE);
+  if (s_bad && q == 0) atomicOr(b.status, OCMPS_ST_CHARGE);
   __syncthreads();
   if (q == 0) {
     DecompWork* w = b.dw;
@@ -85,57 +106,63 @@ __global__ void __launch_bounds__(OCMPS_MAX_Q) decomp_setup_kernel(DecompArgs a,
       }
     }
     w->n = g.n; w->m = g.m; w->ld = g.m; w->mode = g.mode;
-    w->nblocks = nb; w->nvtot = ov; w->newdim = 0; w->norm_count = 0;
+    w->nblocks = nb; w->nvtot = ov; w->newdim = 0; w->scale = 1.0;
   }
-  __syncthreads();
-  // comps / vectors that belong to no block
-  for (int i = q; i < ncomp; i += blockDim.x) { comp_blk[i] = -1; comp_rank[i] = 0; }
   __syncthreads();
   const int mb = blk_of_q[q];
   if (mb >= 0) {
-    int ov = off_v[q], oc = off_c[q], kv = 0, kc = 0;
-    for (int i = 0; i < g.n; ++i) {
-      if (row_charge(a, i) == q) {
-        if (g.mode == 0) { b.comp_idx[oc + kc] = i; comp_blk[i] = mb; comp_rank[i] = kc; ++kc; }
-        else { b.vec_idx[ov + kv] = i; b.vecq[ov + kv] = q; ++kv; }
-      }
-    }
-    for (int j = 0; j < g.m; ++j) {
-      if (col_charge(a, j, chiR) == q) {
-        if (g.mode == 0) { b.vec_idx[ov + kv] = j; b.vecq[ov + kv] = q; ++kv; }
-        else { b.comp_idx[oc + kc] = j; comp_blk[j] = mb; comp_rank[j] = kc; ++kc; }
-      }
-    }
+    const int ov = off_v[q], oc = off_c[q];
+    int kv = 0, kc = 0;
+    for (int i = 0; i < nvec; ++i)
+      if (vq[i] == q) { b.vec_idx[ov + kv] = i; b.vecq[ov + kv] = q; vec_blk[i] = mb; vec_rank[i] = kv; ++kv; }
+    for (int i = 0; i < ncomp; ++i)
+      if (cq[i] == q) { b.comp_idx[oc + kc] = i; comp_blk[i] = mb; comp_rank[i] = kc; ++kc; }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// one-sided Jacobi on one charge block per CTA
+// QR-preconditioned one-sided Jacobi on one charge block per CTA
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+__device__ __forceinline__ double half_sum(double v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
-__global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a, DecompBuffers b, int smem_elems) {
+template <bool SMEM>
+__global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a, DecompBuffers b, int smem_elems, double rank_tol) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_rot;
-  __shared__ double s_part[JAC_THREADS / 32];
-  __shared__ double s_thr;
+  __shared__ int s_rot, s_keff;
+  __shared__ double s_F;
+  __shared__ double s_nrm[JAC_NV_SMEM];
+  __shared__ double s_rdr[JAC_NV_SMEM], s_rdi[JAC_NV_SMEM];   // diagonal of R
+  __shared__ short s_perm[JAC_NV_SMEM];
   const DecompWork* w = b.dw;
   if ((int)blockIdx.x >= w->nblocks) return;
   const DecompBlock B = w->blk[blockIdx.x];
   const int nv = B.nv, len = B.len, ld = w->ld, mode = w->mode;
+  const bool fits = nv * len <= smem_elems && nv <= JAC_NV_SMEM;
+  if (fits != SMEM) return;             // the other instantiation handles this block
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = JAC_THREADS / 32;
-  cplx* Yg = b.ywork + B.ws_off;
-  const bool in_smem = nv * len <= smem_elems;
-  cplx* Y = in_smem ? reinterpret_cast<cplx*>(smem_raw) : Yg;
+  const int half = lane >> 4, hl = lane & 15;
+  cplx* Ya = b.ywork + B.ws_off;                       // region A: final Z (k x nv, physical vector order)
+  cplx* Yb = b.ywork + b.ywork_half + B.ws_off;        // region B: transposition scratch
+  cplx* Y = SMEM ? reinterpret_cast<cplx*>(smem_raw) : Ya;
+  double* nrm = SMEM ? s_nrm : (b.P + B.p_off);        // the fallback keeps its cached norms in global memory
+  double* rdr = SMEM ? s_rdr : (b.scratch_d + 2 * B.p_off);
+  double* rdi = rdr + (SMEM ? JAC_NV_SMEM : nv);
+  if (SMEM) rdi = s_rdi;
+  short* perm = SMEM ? s_perm : reinterpret_cast<short*>(b.scratch_d + 2 * NV_MAX) + B.p_off;
   const int* vidx = b.vec_idx + B.vec_off;
   const int* cidx = b.comp_idx + B.comp_off;
 
-  // gather the block: Y[v][c]
-  if (mode == 0) {   // vectors are columns: consecutive threads take consecutive vectors (coalesced over columns)
+  // ---- phase 0: gather the block, Y[v][c] = component c of vector v ----
+  if (mode == 0) {   // vectors are columns of X: consecutive threads take consecutive vectors (coalesced over columns)
     for (int e = tid; e < nv * len; e += JAC_THREADS) {
       int c = e / nv, v = e % nv;
       Y[v * len + c] = a.X[(size_t)cidx[c] * ld + vidx[v]];
@@ -147,107 +174,213 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
     }
   }
   __syncthreads();
+  for (int v = warp; v < nv; v += nwarps) {
+    const cplx* y = Y + v * len;
+    double s = 0.0;
+    for (int c = lane; c < len; c += 32) { cplx u = y[c]; s += u.x * u.x + u.y * u.y; }
+    s = warp_sum(s);
+    if (lane == 0) { nrm[v] = s; perm[v] = (short)v; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int v = 0; v < nv; ++v) t += nrm[v];
+    s_F = t;
+    s_keff = 0;
+  }
+  __syncthreads();
+  const double F = s_F;
+  const double rtol_abs = F * rank_tol;
 
-  // deflation threshold: vectors whose squared norm falls below 1e-30 of the block's Frobenius norm are
-  // numerically zero (a set of nv > rank vectors can only become mutually orthogonal if the surplus is 0)
-  {
-    double f = 0.0;
-    for (int e = tid; e < nv * len; e += JAC_THREADS) { cplx u = Y[e]; f += u.x * u.x + u.y * u.y; }
-    f = warp_sum(f);
-    if (lane == 0) s_part[warp] = f;
-    __syncthreads();
-    if (tid == 0) {
-      double t = 0.0;
-      for (int i = 0; i < nwarps; ++i) t += s_part[i];
-      s_thr = t * 1e-30;
+  // ---- phase 1: Householder QR with column pivoting, in place; R's strict upper part and rdiag remain ----
+  const int kmax = nv < len ? nv : len;
+  int keff = 0;
+  for (int j = 0; j < kmax; ++j) {
+    // pivot: every warp finds the same argmax of the trailing norms (ties -> smaller position)
+    double best = -1.0; int bpos = j;
+    for (int i = j + lane; i < nv; i += 32) {
+      const double t = nrm[perm[i]];
+      if (t > best) { best = t; bpos = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+      if (ob > best || (ob == best && op < bpos)) { best = ob; bpos = op; }
+    }
+    if (!(best > rtol_abs)) break;         // numerical rank reached: the trailing block is negligible
+    keff = j + 1;
+    const int pv = perm[bpos];             // physical slot of the pivot vector
+    const int pj = perm[j];
+    __syncthreads();                        // everybody has read perm before it is swapped
+    if (tid == 0) { perm[j] = (short)pv; perm[bpos] = (short)pj; }
+    const cplx* x = Y + pv * len;          // Householder vector: x[j..len), with x[j] replaced by v0
+    const cplx alpha = x[j];
+    const double normx = sqrt(best);
+    const double aabs = sqrt(alpha.x * alpha.x + alpha.y * alpha.y);
+    const double phr = aabs > 0.0 ? alpha.x / aabs : 1.0, phi = aabs > 0.0 ? alpha.y / aabs : 0.0;
+    const double v0r = alpha.x + phr * normx, v0i = alpha.y + phi * normx;
+    const double beta = 1.0 / (normx * (normx + aabs));
+    if (tid == 0) { rdr[j] = -phr * normx; rdi[j] = -phi * normx; nrm[pv] = -2.0; }   // R_jj; pivot leaves the candidate set
+    __syncthreads();                        // perm swapped
+    // apply H = I - beta v v^H to the remaining vectors, one half-warp per vector
+    for (int ib = j + 1 + 2 * warp; ib < nv; ib += 2 * nwarps) {
+      const int i = ib + half;
+      const bool act = i < nv;
+      cplx* y = Y + (act ? (int)perm[i] : pv) * len;
+      double wr = 0.0, wi = 0.0;
+      if (act) {
+        for (int c = j + hl; c < len; c += 16) {
+          cplx vv = x[c];
+          if (c == j) { vv.x = v0r; vv.y = v0i; }
+          const cplx yy = y[c];
+          wr += vv.x * yy.x + vv.y * yy.y;      // conj(v) * y
+          wi += vv.x * yy.y - vv.y * yy.x;
+        }
+      }
+      wr = half_sum(wr); wi = half_sum(wi);
+      double tail = 0.0;
+      if (act) {
+        const double fr = beta * wr, fi = beta * wi;
+        for (int c = j + hl; c < len; c += 16) {
+          cplx vv = x[c];
+          if (c == j) { vv.x = v0r; vv.y = v0i; }
+          cplx yy = y[c];
+          yy.x -= fr * vv.x - fi * vv.y;
+          yy.y -= fr * vv.y + fi * vv.x;
+          y[c] = yy;
+          if (c > j) tail += yy.x * yy.x + yy.y * yy.y;
+        }
+      }
+      tail = half_sum(tail);
+      if (act && hl == 0) nrm[perm[i]] = tail;
     }
     __syncthreads();
   }
-  const double thr = s_thr;
+  if (tid == 0) s_keff = keff;
 
-  const int npad = (nv + 1) & ~1;
-  bool converged = (nv < 2);
+  // ---- phase 2: R (keff x nv, position order) -> row-major scratch -> back as the Jacobi working set ----
+  for (int e = tid; e < keff * nv; e += JAC_THREADS) {
+    const int c = e / nv, i = e % nv;
+    cplx v = make_double2(0.0, 0.0);
+    if (i == c) v = make_double2(rdr[c], rdi[c]);
+    else if (i > c) v = Y[(int)perm[i] * len + c];
+    Yb[e] = v;
+  }
+  __syncthreads();
+  cplx* Z = SMEM ? Y : Yb;
+  if (SMEM) {
+    for (int e = tid; e < keff * nv; e += JAC_THREADS) Z[e] = Yb[e];
+    __syncthreads();
+  }
+
+  // ---- phase 3: one-sided Jacobi on the keff rows of R (length nv each) ----
+  const int npad = (keff + 1) & ~1;
+  const int npairs = npad / 2;
+  const double thr = F * DEFLATE_REL;
+  bool converged = false;
   for (int sweep = 0; sweep < JAC_MAX_SWEEPS && !converged; ++sweep) {
+    for (int v = warp; v < keff; v += nwarps) {        // exact Gram diagonal at the start of every sweep
+      const cplx* y = Z + v * nv;
+      double s = 0.0;
+      for (int c = lane; c < nv; c += 32) { cplx u = y[c]; s += u.x * u.x + u.y * u.y; }
+      s = warp_sum(s);
+      if (lane == 0) nrm[v] = s;
+    }
     if (tid == 0) s_rot = 0;
     __syncthreads();
+    if (keff < 2) break;
     for (int r = 0; r < npad - 1; ++r) {
-      for (int k = warp; k < npad / 2; k += nwarps) {
+      for (int kb = 2 * warp; kb < npairs; kb += 2 * nwarps) {     // warp-uniform trip count
+        const int k = kb + half;
         int p = (r + k) % (npad - 1);
         int q = (k == 0) ? (npad - 1) : (r + npad - 1 - k) % (npad - 1);
-        if (p >= nv || q >= nv) continue;
+        const bool act = (k < npairs) && p < keff && q < keff;
         if (p > q) { int tmp = p; p = q; q = tmp; }
-        cplx* yp = Y + p * len;
-        cplx* yq = Y + q * len;
-        double aa = 0.0, bb = 0.0, cre = 0.0, cim = 0.0;
-        for (int c = lane; c < len; c += 32) {
-          cplx u = yp[c], v = yq[c];
-          aa += u.x * u.x + u.y * u.y;
-          bb += v.x * v.x + v.y * v.y;
-          cre += u.x * v.x + u.y * v.y;      // conj(u) * v
-          cim += u.x * v.y - u.y * v.x;
+        cplx* yp = Z + (act ? p : 0) * nv;
+        cplx* yq = Z + (act ? q : 0) * nv;
+        double cre = 0.0, cim = 0.0;
+        if (act) {
+          for (int c = hl; c < nv; c += 16) {
+            cplx u = yp[c], v = yq[c];
+            cre += u.x * v.x + u.y * v.y;      // conj(u) * v
+            cim += u.x * v.y - u.y * v.x;
+          }
         }
-        aa = warp_sum(aa); bb = warp_sum(bb); cre = warp_sum(cre); cim = warp_sum(cim);
+        cre = half_sum(cre); cim = half_sum(cim);
+        if (!act) continue;
+        const double aa = nrm[p], bb = nrm[q];
         const double c2 = cre * cre + cim * cim;
         if (aa <= thr || bb <= thr) {
-          if (aa <= thr && aa > 0.0) for (int c = lane; c < len; c += 32) yp[c] = make_double2(0.0, 0.0);
-          if (bb <= thr && bb > 0.0) for (int c = lane; c < len; c += 32) yq[c] = make_double2(0.0, 0.0);
+          if (aa <= thr && aa > 0.0) { for (int c = hl; c < nv; c += 16) yp[c] = make_double2(0.0, 0.0); if (hl == 0) nrm[p] = 0.0; }
+          if (bb <= thr && bb > 0.0) { for (int c = hl; c < nv; c += 16) yq[c] = make_double2(0.0, 0.0); if (hl == 0) nrm[q] = 0.0; }
         } else if (c2 > JAC_TOL2 * aa * bb) {
-          const double cabs = sqrt(c2);
-          const double zeta = (bb - aa) / (2.0 * cabs);
-          const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double cs = 1.0 / sqrt(1.0 + tt * tt);
+          const double inv_r = rsqrt(c2);
+          const double rr = c2 * inv_r;                         // |c|
+          const double dd = 0.5 * (bb - aa);
+          const double hh = sqrt(dd * dd + c2);
+          const double tt = (dd >= 0.0 ? rr : -rr) / (fabs(dd) + hh);   // tan of the rotation angle
+          const double cs = rsqrt(1.0 + tt * tt);
           const double sn = cs * tt;
-          const double phr = cre / cabs, phi = cim / cabs;       // e^{i phi}
-          // yp' = cs yp - sn conj(ph) yq ;  yq' = sn ph yp + cs yq
-          const double s1r = sn * phr, s1i = sn * phi;
-          for (int c = lane; c < len; c += 32) {
-            cplx u = yp[c], v = yq[c];
-            cplx nu, nvv;
-            nu.x = cs * u.x - (s1r * v.x + s1i * v.y);
-            nu.y = cs * u.y - (s1r * v.y - s1i * v.x);
-            nvv.x = (s1r * u.x - s1i * u.y) + cs * v.x;
-            nvv.y = (s1r * u.y + s1i * u.x) + cs * v.y;
-            yp[c] = nu; yq[c] = nvv;
+          const double phr = cre * inv_r, phi = cim * inv_r;    // e^{i phi} = c / |c|, absorbed into vector q
+          for (int c = hl; c < nv; c += 16) {
+            const cplx u = yp[c], v = yq[c];
+            const double vx = phr * v.x + phi * v.y, vy = phr * v.y - phi * v.x;
+            yp[c] = make_double2(cs * u.x - sn * vx, cs * u.y - sn * vy);
+            yq[c] = make_double2(sn * u.x + cs * vx, sn * u.y + cs * vy);
           }
-          if (lane == 0) s_rot = 1;
+          if (hl == 0) {
+            const double na = aa - tt * rr, nb = bb + tt * rr;
+            nrm[p] = na > 0.0 ? na : 0.0;
+            nrm[q] = nb > 0.0 ? nb : 0.0;
+            s_rot = 1;
+          }
         }
       }
       __syncthreads();
     }
     converged = (s_rot == 0);
+    if (tid == 0) { atomicAdd(&g_jac_dbg[0], 1ull); atomicMax(&g_jac_dbg[2], (unsigned long long)(sweep + 1)); if (nv >= 64) atomicAdd(&g_jac_dbg[3], 1ull); if (nv >= 64 && sweep == 0) atomicAdd(&g_jac_dbg[4], 1ull); }
     __syncthreads();
     if (!converged && sweep == JAC_MAX_SWEEPS - 1 && tid == 0) atomicOr(b.status, OCMPS_ST_NOCONV);
   }
+  if (tid == 0) atomicAdd(&g_jac_dbg[1], 1ull);
 
-  // spectrum + normalised vectors
+  // ---- phase 4: spectrum + normalised right vectors Z[j][physical vector] ----
+  __syncthreads();
   for (int v = warp; v < nv; v += nwarps) {
-    cplx* y = Y + v * len;
-    double s = 0.0;
-    for (int c = lane; c < len; c += 32) { cplx u = y[c]; s += u.x * u.x + u.y * u.y; }
-    s = warp_sum(s);
-    const double inv = s > 0.0 ? 1.0 / sqrt(s) : 0.0;
-    for (int c = lane; c < len; c += 32) {
-      cplx u = y[c];
-      Yg[v * len + c] = make_double2(u.x * inv, u.y * inv);
+    if (v < keff) {
+      const cplx* y = Z + v * nv;
+      double s = 0.0;
+      for (int c = lane; c < nv; c += 32) { cplx u = y[c]; s += u.x * u.x + u.y * u.y; }
+      s = warp_sum(s);
+      const double inv = s > 0.0 ? rsqrt(s) : 0.0;
+      for (int c = lane; c < nv; c += 32) {
+        cplx u = y[c];
+        Ya[v * nv + (int)perm[c]] = make_double2(u.x * inv, u.y * inv);
+      }
+      __syncwarp();
+      if (lane == 0) b.P[B.p_off + v] = s;
+    } else if (lane == 0) {
+      b.P[B.p_off + v] = 0.0;
     }
-    if (lane == 0) b.P[B.p_off + v] = s;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// global truncation (ITensor truncate()) + new bond bookkeeping + follow-up descriptors
+// global truncation (ITensor truncate()) + new bond bookkeeping + follow-up descriptor
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) truncate_kernel(DecompArgs a, DecompBuffers b, TruncParams tp) {
   __shared__ double sP[NV_MAX];
   __shared__ double sSorted[NV_MAX];
-  __shared__ int sQ[NV_MAX];
+  __shared__ short sQ[NV_MAX];
   __shared__ unsigned char sKeep[NV_MAX];
   __shared__ double s_docut;
   __shared__ int s_total;
   DecompWork* w = b.dw;
   const int nv = w->nvtot;
   const int tid = threadIdx.x;
-  for (int i = tid; i < nv; i += blockDim.x) { sP[i] = b.P[i]; sQ[i] = b.vecq[i]; }
+  for (int i = tid; i < nv; i += blockDim.x) { sP[i] = b.P[i]; sQ[i] = (short)b.vecq[i]; }
   if (tid == 0) s_total = 0;
   __syncthreads();
   for (int i = tid; i < nv; i += blockDim.x) {
@@ -314,8 +447,7 @@ __global__ void __launch_bounds__(1024) truncate_kernel(DecompArgs a, DecompBuff
       }
       if (pos < tp.cap) {
         a.qNew[pos] = qi;
-        // block of vector i: scan the (short) block table
-        int bi = 0;
+        int bi = 0;                      // block of vector i: scan the (short) block table
         while (bi + 1 < w->nblocks && w->blk[bi + 1].p_off <= i) ++bi;
         inv_blk[pos] = bi;
         inv_v[pos] = i - w->blk[bi].p_off;
@@ -328,67 +460,112 @@ __global__ void __launch_bounds__(1024) truncate_kernel(DecompArgs a, DecompBuff
     if (k > tp.cap) { atomicOr(b.status, OCMPS_ST_CAPACITY); k = tp.cap; }
     w->newdim = k;
     *a.dimNew = k;
-    const int n = w->n, m = w->m;
-    GemmDesc g0, g1;
-    g0.pad = g1.pad = 0;
-    g1.A = g1.B = nullptr; g1.C = nullptr; g1.M = g1.N = g1.K = 0; g1.lda = g1.ldb = g1.ldc = 1; g1.opA = g1.opB = 0;
-    switch (a.kind) {
-      case DK_GATE_LEFT:   // partner (k x m) = iso^H (n x k) . X (n x m)
-      case DK_ORTH_LEFT:
-        g0.A = a.iso; g0.opA = 1; g0.lda = k;
-        g0.B = a.X; g0.opB = 0; g0.ldb = m;
-        g0.C = a.partner; g0.ldc = m; g0.M = k; g0.N = m; g0.K = n;
-        w->norm_count = k * m;
-        if (a.kind == DK_ORTH_LEFT) {     // neighbour (k x D*chiFar) = C (k x m) . nb_in (m x D*chiFar)
-          const int far = a.D * (*a.dimNb);
-          g1.A = a.partner; g1.opA = 0; g1.lda = m;
-          g1.B = a.nb_in; g1.opB = 0; g1.ldb = far;
-          g1.C = a.nb_out; g1.ldc = far; g1.M = k; g1.N = far; g1.K = m;
-        }
-        break;
-      default:             // partner (n x k) = X (n x m) . iso^H (k x m)^H
-        g0.A = a.X; g0.opA = 0; g0.lda = m;
-        g0.B = a.iso; g0.opB = 1; g0.ldb = m;
-        g0.C = a.partner; g0.ldc = k; g0.M = n; g0.N = k; g0.K = m;
-        w->norm_count = n * k;
-        if (a.kind == DK_ORTH_RIGHT) {    // neighbour (chiFar*D x k) = nb_in (chiFar*D x n) . C (n x k)
-          const int far = a.D * (*a.dimNb);
-          g1.A = a.nb_in; g1.opA = 0; g1.lda = n;
-          g1.B = a.partner; g1.opB = 0; g1.ldb = k;
-          g1.C = a.nb_out; g1.ldc = k; g1.M = far; g1.N = k; g1.K = n;
-        }
-        break;
+    // Frobenius norm of the tensor that carries the centre = sqrt(sum of kept weights), fixed summation order
+    double kept = 0.0;
+    for (int i = 0; i < nv; ++i) if (sKeep[i] && b.pos[i] < tp.cap) kept += sP[i];
+    double scale = 1.0;
+    if (tp.normalize) {
+      const double nrm = sqrt(kept);
+      if (nrm > 1e-16) scale = 1.0 / nrm;      // src/BH_tDMRG.cpp:183-184
     }
-    b.descs[0] = g0;
+    w->scale = scale;
+    const int n = w->n, m = w->m;
+    GemmDesc g1;
+    g1.pad = 0;
+    g1.A = g1.B = nullptr; g1.C = nullptr; g1.M = g1.N = g1.K = 0; g1.lda = g1.ldb = g1.ldc = 1; g1.opA = g1.opB = 0;
+    if (a.kind == DK_ORTH_LEFT) {        // neighbour (k x D*chiFar) = C (k x m) . nb_in (m x D*chiFar)
+      const int far = a.D * (*a.dimNb);
+      g1.A = a.partner; g1.opA = 0; g1.lda = m;
+      g1.B = a.nb_in; g1.opB = 0; g1.ldb = far;
+      g1.C = a.nb_out; g1.ldc = far; g1.M = k; g1.N = far; g1.K = m;
+    } else if (a.kind == DK_ORTH_RIGHT) { // neighbour (chiFar*D x k) = nb_in (chiFar*D x n) . C (n x k)
+      const int far = a.D * (*a.dimNb);
+      g1.A = a.nb_in; g1.opA = 0; g1.lda = n;
+      g1.B = a.partner; g1.opB = 0; g1.ldb = k;
+      g1.C = a.nb_out; g1.ldc = k; g1.M = far; g1.N = k; g1.K = n;
+    }
     b.descs[1] = g1;
   }
 }
 
-// isometry assembly: every output element looks up its source (no zero-fill pass, coalesced writes)
-__global__ void scatter_iso_kernel(DecompArgs a, DecompBuffers b) {
+// ------------------------------------------------------------------------------------------------
+// assembly of the two factors, one CTA per kept state j:
+//   isometry  u_j = M z_j^H / |M z_j^H|  (scattered into column / row j, zero outside the charge block)
+//   partner   sigma_j z_j * scale         (the tensor that carries the orthogonality centre)
+// ------------------------------------------------------------------------------------------------
+constexpr int BUILD_THREADS = 256;
+__global__ void __launch_bounds__(BUILD_THREADS) build_factors_kernel(DecompArgs a, DecompBuffers b) {
+  extern __shared__ __align__(16) unsigned char bsm[];
+  __shared__ double red[BUILD_THREADS / 32];
+  __shared__ double s_inv;
   const DecompWork* w = b.dw;
-  const int k = w->newdim, n = w->n, m = w->m, mode = w->mode;
+  const int k = w->newdim;
+  const int kk = blockIdx.x;
+  if (kk >= k) return;
+  const int n = w->n, m = w->m, ld = w->ld, mode = w->mode;
   const int* comp_blk = b.comp_idx + NV_MAX;
   const int* comp_rank = b.comp_idx + 2 * NV_MAX;
-  const int* inv_blk = b.pos + NV_MAX;
-  const int* inv_v = b.pos + 2 * NV_MAX;
-  const long long total = (long long)(mode == 0 ? n : m) * k;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    int comp, kk;
-    if (mode == 0) { comp = (int)(e / k); kk = (int)(e % k); }      // iso[n][k]
-    else { kk = (int)(e / m); comp = (int)(e % m); }                // iso[k][m]
-    cplx v = make_double2(0.0, 0.0);
-    const int bi = inv_blk[kk];
-    if (comp_blk[comp] == bi) {
-      const DecompBlock& B = w->blk[bi];
-      v = b.ywork[B.ws_off + inv_v[kk] * B.len + comp_rank[comp]];
+  const int* vec_blk = b.vec_idx + NV_MAX;
+  const int* vec_rank = b.vec_idx + 2 * NV_MAX;
+  const int bi = b.pos[NV_MAX + kk], j = b.pos[2 * NV_MAX + kk];
+  const DecompBlock B = w->blk[bi];
+  const int nv = B.nv, len = B.len;
+  const int* vidx = b.vec_idx + B.vec_off;
+  const int* cidx = b.comp_idx + B.comp_off;
+  const cplx* Zj = b.ywork + B.ws_off + (size_t)j * nv;
+  const double sigma = sqrt(b.P[B.p_off + j]) * w->scale;
+  cplx* zs = reinterpret_cast<cplx*>(bsm);            // z_j (nv)
+  cplx* out = zs + nv;                                // M z_j^H (len)
+  const int tid = threadIdx.x;
+  for (int v = tid; v < nv; v += BUILD_THREADS) zs[v] = Zj[v];
+  __syncthreads();
+  double part = 0.0;
+  for (int c = tid; c < len; c += BUILD_THREADS) {
+    double sr = 0.0, si = 0.0;
+    if (mode == 0) {
+      const cplx* row = a.X + (size_t)cidx[c] * ld;
+      for (int v = 0; v < nv; ++v) {
+        const cplx x = row[vidx[v]], z = zs[v];
+        sr += x.x * z.x + x.y * z.y;          // x * conj(z)
+        si += x.y * z.x - x.x * z.y;
+      }
+    } else {
+      const int col = cidx[c];
+      for (int v = 0; v < nv; ++v) {
+        const cplx x = a.X[(size_t)vidx[v] * ld + col], z = zs[v];
+        sr += x.x * z.x + x.y * z.y;
+        si += x.y * z.x - x.x * z.y;
+      }
     }
-    a.iso[e] = v;
+    out[c] = make_double2(sr, si);
+    part += sr * sr + si * si;
+  }
+  part = warp_sum(part);
+  if ((tid & 31) == 0) red[tid >> 5] = part;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int i = 0; i < BUILD_THREADS / 32; ++i) t += red[i];
+    s_inv = t > 0.0 ? rsqrt(t) : 0.0;
+  }
+  __syncthreads();
+  const double inv = s_inv;
+  // isometry: element (component, kk); partner: element (vector, kk)
+  const int ncomp = mode == 0 ? n : m, nvec = mode == 0 ? m : n;
+  for (int c = tid; c < ncomp; c += BUILD_THREADS) {
+    cplx v = make_double2(0.0, 0.0);
+    if (comp_blk[c] == bi) { const cplx o = out[comp_rank[c]]; v = make_double2(o.x * inv, o.y * inv); }
+    if (mode == 0) a.iso[(size_t)c * k + kk] = v; else a.iso[(size_t)kk * m + c] = v;
+  }
+  for (int v = tid; v < nvec; v += BUILD_THREADS) {
+    cplx o = make_double2(0.0, 0.0);
+    if (vec_blk[v] == bi) { const cplx z = zs[vec_rank[v]]; o = make_double2(z.x * sigma, z.y * sigma); }
+    if (mode == 0) a.partner[(size_t)kk * m + v] = o; else a.partner[(size_t)v * k + kk] = o;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Frobenius normalisation, deterministic two-stage reduction
+// Frobenius normalisation of one site tensor, deterministic two-stage reduction
 // ------------------------------------------------------------------------------------------------
 constexpr int NORM_CTAS = 32;
 constexpr int NORM_THREADS = 256;
@@ -412,20 +589,6 @@ __device__ __forceinline__ double norm_total(const double* partial) {
   double s = 0.0;
   for (int i = 0; i < NORM_CTAS; ++i) s += partial[i];
   return s;
-}
-
-__global__ void __launch_bounds__(NORM_THREADS) norm_partial_dw_kernel(const cplx* x, const DecompWork* w, double* partial) {
-  norm_partial_body(x, w->norm_count, partial);
-}
-__global__ void scale_dw_kernel(cplx* x, const DecompWork* w, const double* partial) {
-  const double nrm = sqrt(norm_total(partial));
-  if (!(nrm > 1e-16)) return;          // src/BH_tDMRG.cpp:184
-  const double inv = 1.0 / nrm;
-  const long long count = w->norm_count;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x) {
-    cplx u = x[e];
-    x[e] = make_double2(u.x * inv, u.y * inv);
-  }
 }
 __global__ void __launch_bounds__(NORM_THREADS) norm_partial_site_kernel(const cplx* x, const int* dimL, const int* dimR, int D,
                                                                         double* partial) {
@@ -456,31 +619,35 @@ int grid_for(long long elems, int threads, int cap = 1184) {
 
 static bool g_jac_attr_set[64] = {false};
 
+void debug_jacobi_counters(unsigned long long* out, bool reset) {
+  cudaMemcpyFromSymbol(out, g_jac_dbg, sizeof(unsigned long long) * 8);
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_jac_dbg, z, sizeof(z)); }
+}
+
 void launch_decomp_setup(const DecompArgs& a, const DecompBuffers& b, cudaStream_t s) {
   decomp_setup_kernel<<<1, OCMPS_MAX_Q, 0, s>>>(a, b);
 }
 
-void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_launch, size_t smem_limit, cudaStream_t s) {
+void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_launch, size_t smem_limit, bool need_global,
+                          double rank_tol, cudaStream_t s) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !g_jac_attr_set[dev]) {
-    cudaFuncSetAttribute(jacobi_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(jacobi_blocks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(build_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     g_jac_attr_set[dev] = true;
   }
-  jacobi_blocks_kernel<<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)));
+  jacobi_blocks_kernel<true><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
+  if (need_global) jacobi_blocks_kernel<false><<<nblk_launch, JAC_THREADS, 0, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
 }
 
 void launch_truncate(const DecompArgs& a, const DecompBuffers& b, const TruncParams& tp, cudaStream_t s) {
   truncate_kernel<<<1, 1024, 0, s>>>(a, b, tp);
 }
 
-void launch_scatter_iso(const DecompArgs& a, const DecompBuffers& b, int max_elems, cudaStream_t s) {
-  scatter_iso_kernel<<<grid_for(max_elems, 256), 256, 0, s>>>(a, b);
-}
-
-void launch_normalize(cplx* x, const DecompBuffers& b, int max_elems, cudaStream_t s) {
-  norm_partial_dw_kernel<<<NORM_CTAS, NORM_THREADS, 0, s>>>(x, b.dw, b.partial);
-  scale_dw_kernel<<<grid_for(max_elems, 256), 256, 0, s>>>(x, b.dw, b.partial);
+void launch_build_factors(const DecompArgs& a, const DecompBuffers& b, int cap_k, int cap_vec, int cap_comp, cudaStream_t s) {
+  const size_t sm = sizeof(cplx) * (size_t)(cap_vec + cap_comp);
+  build_factors_kernel<<<cap_k, BUILD_THREADS, sm, s>>>(a, b);
 }
 
 void launch_norm_only(const cplx* x, const int* dimL, const int* dimR, int D, double* partial, double* out, int max_elems,

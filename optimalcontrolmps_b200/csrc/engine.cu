@@ -187,12 +187,14 @@ int alloc_ws(ocmps_ctx* ctx, int L, int D, int cap, bool with_work, Workspace** 
   CK(cudaMalloc(&w->theta, sizeof(cplx) * nD * nD));
   CK(cudaMalloc(&w->cbuf, sizeof(cplx) * (size_t)cap * cap));
   CK(cudaMalloc(&w->db.dw, sizeof(DecompWork)));
-  CK(cudaMalloc(&w->db.vec_idx, sizeof(int) * NV_MAX));
+  CK(cudaMalloc(&w->db.vec_idx, sizeof(int) * 3 * NV_MAX));
   CK(cudaMalloc(&w->db.comp_idx, sizeof(int) * 3 * NV_MAX));
   CK(cudaMalloc(&w->db.vecq, sizeof(int) * NV_MAX));
   CK(cudaMalloc(&w->db.P, sizeof(double) * NV_MAX));
   CK(cudaMalloc(&w->db.pos, sizeof(int) * 3 * NV_MAX));
-  CK(cudaMalloc(&w->db.ywork, sizeof(cplx) * nD * cap));
+  CK(cudaMalloc(&w->db.ywork, sizeof(cplx) * 2 * nD * cap));
+  w->db.ywork_half = (long long)(nD * cap);
+  CK(cudaMalloc(&w->db.scratch_d, sizeof(double) * 3 * NV_MAX));
   CK(cudaMalloc(&w->db.descs, sizeof(GemmDesc) * 4));
   CK(cudaMalloc(&w->db.partial, sizeof(double) * 64));
   CK(cudaMalloc(&w->d_norm, sizeof(double) * 4));
@@ -223,7 +225,7 @@ void free_ws(Workspace* w) {
   if (!w) return;
   cudaFree(w->theta); cudaFree(w->cbuf); cudaFree(w->db.dw); cudaFree(w->db.vec_idx); cudaFree(w->db.comp_idx);
   cudaFree(w->db.vecq); cudaFree(w->db.P); cudaFree(w->db.pos); cudaFree(w->db.ywork); cudaFree(w->db.descs);
-  cudaFree(w->db.partial); cudaFree(w->d_norm);
+  cudaFree(w->db.partial); cudaFree(w->d_norm); cudaFree(w->db.scratch_d);
   cudaFree(w->E[0]); cudaFree(w->E[1]); cudaFree(w->T); cudaFree(w->odescs); cudaFree(w->d_out);
   free_mps(w->work); free_mps(w->big);
   if (w->bigws) free_ws(w->bigws);
@@ -368,17 +370,22 @@ std::vector<Op> build_schedule(int L) {
 // ------------------------------------------------------------------------------------------------
 // decomposition driver
 // ------------------------------------------------------------------------------------------------
-void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int capV, int capC, int maxIso, cudaStream_t s) {
+// setup -> QR + Jacobi per charge block -> global truncation -> assembly of isometry and centre factor
+void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int capV, int capC, int capK, cudaStream_t s) {
   launch_decomp_setup(a, ws->db, s);
   // shared memory: the largest block has at most capV vectors of at most capC components
   size_t need = (size_t)capV * capC * sizeof(cplx);
   size_t smem = std::min(need, JAC_SMEM_LIMIT);
   if (smem < 1024) smem = 1024;
   int nblk = std::min(OCMPS_MAX_BLK, std::max(capV, capC) + a.D);
-  launch_jacobi_blocks(a, ws->db, nblk, smem, s);
+  const bool need_global = need > JAC_SMEM_LIMIT;    // some block may not fit in shared memory
+  // numerical-rank tolerance of the pivoted QR: the neglected weight stays >= 6 orders below the cutoff
+  double rank_tol = 1e-8 * tp.cutoff;
+  rank_tol = std::min(1e-16, std::max(1e-30, rank_tol));
+  launch_jacobi_blocks(a, ws->db, nblk, smem, need_global, rank_tol, s);
   launch_truncate(a, ws->db, tp, s);
-  launch_scatter_iso(a, ws->db, maxIso, s);
-  g_ocmps_launches += 4;
+  launch_build_factors(a, ws->db, capK, capV, capC, s);
+  g_ocmps_launches += 4 + (need_global ? 1 : 0);
 }
 
 void phases_of(int D, double U, double tstep, double* re, double* im) {
@@ -398,8 +405,8 @@ void run_step(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, double from, doubl
   phases_of(D, forward ? from : -from, st->tstep, u1r, u1i);   // :116-123
   phases_of(D, forward ? to : -to, st->tstep, u2r, u2i);
   const cplx* G = st->d_G[forward ? 0 : 1];
-  TruncParams tpg{st->cutoff, st->maxm, 1, st->rel_cutoff, 0};
-  TruncParams tpo{MIN_CUT, MAX_M, 1, 0, 0};
+  TruncParams tpg{st->cutoff, st->maxm, 1, st->rel_cutoff, 0, 1};
+  TruncParams tpo{MIN_CUT, MAX_M, 1, 0, 0, 0};
 
   for (int oi = op_begin; oi < (int)st->ops.size() && oi < op_end; ++oi) {
     const Op& op = st->ops[oi];
@@ -442,12 +449,10 @@ void run_step(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, double from, doubl
       // vectors per block <= chi of their own side, components <= chi of the other side
       const int capV = op.c == 0 ? lay.capb[br] : lay.capb[bl];
       const int capC = op.c == 0 ? lay.capb[bl] : lay.capb[br];
-      run_decomp(ws, a, tpg, capV, capC, (op.c == 0 ? n_cap : m_cap) * lay.capb[bm], s);
-      if (op.c == 0) launch_zgemm(ws->db.descs, 1, lay.capb[bm], m_cap, s);
-      else launch_zgemm(ws->db.descs, 1, n_cap, lay.capb[bm], s);
-      launch_normalize(a.partner, ws->db, (op.c == 0 ? m_cap : n_cap) * lay.capb[bm], s);   // :183-184,195-196
+      (void)n_cap; (void)m_cap;
+      run_decomp(ws, a, tpg, capV, capC, lay.capb[bm], s);    // includes the normalisation of :183-184,195-196
       m->cur[j1] ^= 1; m->cur[j2] ^= 1;
-      g_ocmps_launches += 6;
+      g_ocmps_launches += 3;
     } else if (op.kind == 2) {
       const int b = op.a;                                  // bond between sites b and b+1 (1-based) = bond index b
       DecompArgs a;
@@ -461,8 +466,7 @@ void run_step(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, double from, doubl
         a.dimL = m->dim(b - 1); a.dimR = m->dim(b); a.qL = m->q(b - 1); a.qR = m->q(b);
         a.X = m->site(j); a.iso = m->other(j);
         a.nb_in = m->site(jn); a.nb_out = m->other(jn); a.dimNb = m->dim(b + 1);
-        run_decomp(ws, a, tpo, lay.capb[b], lay.capb[b - 1], lay.capb[b - 1] * D * lay.capb[b], s);
-        launch_zgemm(ws->db.descs, 1, lay.capb[b], lay.capb[b], s);
+        run_decomp(ws, a, tpo, lay.capb[b], lay.capb[b - 1], lay.capb[b], s);
         launch_zgemm(ws->db.descs + 1, 1, lay.capb[b], D * lay.capb[b + 1], s);
         m->cur[j] ^= 1; m->cur[jn] ^= 1;
       } else {                    // right: SVD of site b+1 (0-based b), U.S pushed into site b
@@ -471,12 +475,11 @@ void run_step(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, double from, doubl
         a.dimL = m->dim(b); a.dimR = m->dim(b + 1); a.qL = m->q(b); a.qR = m->q(b + 1);
         a.X = m->site(j); a.iso = m->other(j);
         a.nb_in = m->site(jn); a.nb_out = m->other(jn); a.dimNb = m->dim(b - 1);
-        run_decomp(ws, a, tpo, lay.capb[b], lay.capb[b + 1], lay.capb[b] * D * lay.capb[b + 1], s);
-        launch_zgemm(ws->db.descs, 1, lay.capb[b], lay.capb[b], s);
+        run_decomp(ws, a, tpo, lay.capb[b], lay.capb[b + 1], lay.capb[b], s);
         launch_zgemm(ws->db.descs + 1, 1, lay.capb[b - 1] * D, lay.capb[b], s);
         m->cur[j] ^= 1; m->cur[jn] ^= 1;
       }
-      g_ocmps_launches += 2;
+      g_ocmps_launches += 1;
     } else {
       const int j = op.a - 1;
       launch_normalize_site(m->site(j), m->dim(j), m->dim(j + 1), D, ws->db.partial, lay.capb[j] * D * lay.capb[j + 1], s);
@@ -602,7 +605,7 @@ int apply_K_async(ocmps_stepper* st, Workspace* ws, ocmps_mps* in, ocmps_mps* ou
   }
   g_ocmps_launches += L;
   // left-canonicalise the exact product (numerical-rank drops only)
-  TruncParams tpl{MIN_CUT, MAX_M, 1, 1, 0};
+  TruncParams tpl{MIN_CUT, MAX_M, 1, 1, 0, 0};
   for (int b = 1; b <= L - 1; ++b) {
     const int j = b - 1, jn = b;
     DecompArgs a;
@@ -612,14 +615,13 @@ int apply_K_async(ocmps_stepper* st, Workspace* ws, ocmps_mps* in, ocmps_mps* ou
     a.X = big->site(j); a.iso = big->other(j);
     a.nb_in = big->site(jn); a.nb_out = big->other(jn); a.dimNb = big->dim(b + 1);
     tpl.cap = lb.capb[b];
-    run_decomp(bw, a, tpl, lb.capb[b], lb.capb[b - 1], lb.capb[b - 1] * D * lb.capb[b], s);
-    launch_zgemm(bw->db.descs, 1, lb.capb[b], lb.capb[b], s);
+    run_decomp(bw, a, tpl, lb.capb[b], lb.capb[b - 1], lb.capb[b], s);
     launch_zgemm(bw->db.descs + 1, 1, lb.capb[b], D * lb.capb[b + 1], s);
     big->cur[j] ^= 1; big->cur[jn] ^= 1;
-    g_ocmps_launches += 2;
+    g_ocmps_launches += 1;
   }
   // right-to-left compression with the stepper's Cutoff / Maxm (exactApplyMPO defaults: Cutoff 1e-13)
-  TruncParams tpr{st->has_cutoff ? st->cutoff : 1e-13, st->has_maxm ? st->maxm : MAX_M, 1, st->rel_cutoff, 0};
+  TruncParams tpr{st->has_cutoff ? st->cutoff : 1e-13, st->has_maxm ? st->maxm : MAX_M, 1, st->rel_cutoff, 0, 0};
   for (int b = L - 1; b >= 1; --b) {
     const int j = b, jn = b - 1;
     DecompArgs a;
@@ -629,11 +631,10 @@ int apply_K_async(ocmps_stepper* st, Workspace* ws, ocmps_mps* in, ocmps_mps* ou
     a.X = big->site(j); a.iso = big->other(j);
     a.nb_in = big->site(jn); a.nb_out = big->other(jn); a.dimNb = big->dim(b - 1);
     tpr.cap = std::min(lb.capb[b], out->lay.capb[b]);
-    run_decomp(bw, a, tpr, lb.capb[b], lb.capb[b + 1], lb.capb[b] * D * lb.capb[b + 1], s);
-    launch_zgemm(bw->db.descs, 1, lb.capb[b], lb.capb[b], s);
+    run_decomp(bw, a, tpr, lb.capb[b], lb.capb[b + 1], tpr.cap, s);
     launch_zgemm(bw->db.descs + 1, 1, lb.capb[b - 1] * D, lb.capb[b], s);
     big->cur[j] ^= 1; big->cur[jn] ^= 1;
-    g_ocmps_launches += 2;
+    g_ocmps_launches += 1;
   }
   // compact into the chi_cap layout
   for (int j = 0; j < L; ++j) out->cur[j] = 0;
@@ -894,6 +895,8 @@ int ocmps_step(ocmps_stepper* st, ocmps_mps* psi, double from, double to, int fo
   CK(cudaGetLastError());
   return check_status(st->ctx);
 }
+
+int ocmps_debug_jacobi(unsigned long long* out, int reset) { cudaDeviceSynchronize(); debug_jacobi_counters(out, reset != 0); return 0; }
 
 // development aid: run ops [op_begin, op_end) of one step (not part of include/ocmps.h)
 int ocmps_debug_run_ops(ocmps_stepper* st, ocmps_mps* psi, double from, double to, int forward, int op_begin, int op_end) {

@@ -41,7 +41,8 @@ struct DecompWork {
   int n, m, ld;             // matrix X is n x m, leading dimension ld
   int mode;                 // 0: vectors are columns (isometry n x k); 1: vectors are rows (isometry k x m)
   int nblocks, nvtot, newdim;
-  int norm_count;           // number of elements of the tensor to normalise after the decomposition
+  int pad0;
+  double scale;             // factor applied to the centre-carrying factor (1/norm for gate decompositions)
   DecompBlock blk[OCMPS_MAX_BLK];
 };
 
@@ -50,6 +51,7 @@ struct TruncParams {
   int maxm, minm;
   int rel_cutoff;           // ITensor doRelCutoff
   int cap;                  // capacity of the new bond
+  int normalize;            // divide the centre-carrying factor by its Frobenius norm (src/BH_tDMRG.cpp:183-184)
 };
 
 struct SitePtrs { cplx* p[OCMPS_MAX_L]; };
@@ -59,6 +61,8 @@ struct SiteOffs { long long o[OCMPS_MAX_L + 1]; };
 struct Phases { double re[4][OCMPS_MAX_D]; double im[4][OCMPS_MAX_D]; };
 
 extern long long g_ocmps_launches;   // kernels launched so far (bench.py reports it)
+
+void debug_jacobi_counters(unsigned long long* out, bool reset);
 
 // ---- kernels (launchers) ----
 void launch_zgemm(const GemmDesc* d_descs, int batch, int maxM, int maxN, cudaStream_t s);
@@ -88,17 +92,19 @@ struct DecompBuffers {
   int* vecq;                      // charge per entry of P
   double* P;                      // squared norms of all vectors
   int* pos;                       // new bond index of each vector (-1: dropped)
-  cplx* ywork;                    // orthonormalised vectors, block after block
-  GemmDesc* descs;                // [0] partner gemm, [1] neighbour gemm
+  cplx* ywork;                    // region A: right vectors Z block after block; region B (+ywork_half): scratch
+  long long ywork_half;
+  double* scratch_d;              // 3*NV_MAX doubles (global-memory fallback of the block kernel)
+  GemmDesc* descs;                // [1] neighbour gemm of gauge moves, [2] two-site merge
   double* partial;                // norm partial sums
   int* status;
 };
 
 void launch_decomp_setup(const DecompArgs& a, const DecompBuffers& b, cudaStream_t s);
-void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_launch, size_t smem_limit, cudaStream_t s);
+void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_launch, size_t smem_limit, bool need_global,
+                          double rank_tol, cudaStream_t s);
 void launch_truncate(const DecompArgs& a, const DecompBuffers& b, const TruncParams& tp, cudaStream_t s);
-void launch_scatter_iso(const DecompArgs& a, const DecompBuffers& b, int max_elems, cudaStream_t s);
-void launch_normalize(cplx* x, const DecompBuffers& b, int max_elems, cudaStream_t s);   // x /= ||x|| using dw->norm_count
+void launch_build_factors(const DecompArgs& a, const DecompBuffers& b, int cap_k, int cap_vec, int cap_comp, cudaStream_t s);
 
 // merge setup: fills desc for theta = A1 (chil*D x chim) * A2 (chim x D*chir)
 void launch_merge_setup(GemmDesc* d, const cplx* A1, const cplx* A2, cplx* theta, const int* dimL, const int* dimM,

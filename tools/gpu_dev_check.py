@@ -22,7 +22,8 @@ def run(L, d, Npart, J, cs, ce, T, ts, cutoff, maxm, hess=True, seed=1):
     args_o = ob.TruncArgs(cutoff=cutoff, maxm=maxm)
     st_o = ob.BHStepper(L, D, J, ts, args_o)
     a = oc.Args("Cutoff=", cutoff) if maxm is None else oc.Args("Cutoff=", cutoff, "Maxm=", maxm)
-    st = oc.BH_tDMRG(oc.BoseHubbard(L, d), J, ts, a)
+    cap = None if maxm is None else max([maxm] + psi_i.bond_dims() + psi_f.bond_dims())
+    st = oc.BH_tDMRG(oc.BoseHubbard(L, d), J, ts, a, chi_cap=cap)
     print("gate diff", np.abs(st.gate(True) - st_o.G_fwd).max(), np.abs(st.gate(False) - st_o.G_bwd).max())
     # single steps
     rng = np.random.default_rng(seed)
