@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- cost+gradient evaluations per second of the Bose-Hubbard optimal-control hot path.
+
+Workload (BASELINE.json configs[1], "cfg2"): BH chain L=20, Npart=20, d=5 (local dimension 6), J=1,
+T=2.0, tstep=0.01 (Nt=201 time points), GROUP basis with M=10 chopped sines on a linsigmoid ramp
+U: 2.5 -> 50, Maxm=100, Cutoff=1e-8, gamma=1e-6.  One "step" = one cost+gradient evaluation with the
+reference's protocol (main/TestRuntimes.cpp:57-58): getAnalyticGradient(c, new_control=true) followed by
+getCost(c, new_control=false): forward sweep + backward sweep (400 Trotter steps), Nt MPO overlaps, the
+fidelity overlaps and the basis projections.  Controls are synthetic (seeded); psi_init / psi_target are
+the DMRG ground-state fixtures shipped in optimalcontrolmps_b200/data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--hessian-nt NT]
+
+N>1 (torchrun): every rank evaluates its own control on its own GPU (independent units, weak scaling);
+the (cost, gradient) tuples are combined with one NCCL all-gather.  --impl reference times the CPU
+restatement of the reference (oracle/, NumPy/OpenBLAS on all host cores) on a bounded sample of the same
+workload; the reference's own ITensor build cannot be produced here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+CFG = dict(L=20, d=5, Npart=20, J=1.0, T=2.0, tstep=0.01, M=10, maxm=100, cutoff=1e-8, gamma=1e-6, U_i=2.5, U_f=50.0)
+METRIC = "cost+gradient evals/s (BH N=20 chi=100)"
+UNIT = "evals/s"
+
+
+def nt():
+    return int(CFG["T"] / CFG["tstep"] + 1)
+
+
+def make_problem_host(seed):
+    """Basis and coefficient vector of the synthetic control for `seed` (pure host math, shared by both arms)."""
+    import optimalcontrolmps_b200 as oc
+    rng = np.random.default_rng(1000 + seed)
+    u0 = oc.SeedGenerator.linsigmoidSeed(CFG["U_i"], CFG["U_f"], nt(), np.random.default_rng(7))
+    basis = oc.ControlBasisFactory.buildChoppedSineBasis(u0, CFG["tstep"], CFG["T"], CFG["M"])
+    c = np.array(oc.SeedGenerator.randomCoeffSeed(-4.0, 4.0, CFG["M"], rng))     # range of tests/GradientTests.cpp:199
+    for _ in range(40):          # keep every u_i inside the optimiser's box [2, 100] (src/BH_nlp.cpp:55-56)
+        u = np.array(basis.convertControl(list(c)))
+        if u.min() >= 2.0 and u.max() <= 100.0:
+            break
+        c *= 0.8
+    return basis, c, np.array(basis.convertControl(list(c)))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port, bounded sample
+# ----------------------------------------------------------------------------------------------
+def oracle_states():
+    from oracle import bh_mps as ob
+    from optimalcontrolmps_b200.states import ground_state
+    gi = ground_state(CFG["L"], CFG["d"], CFG["Npart"], CFG["U_i"])
+    gf = ground_state(CFG["L"], CFG["d"], CFG["Npart"], CFG["U_f"])
+    conv = lambda h: ob.MPS(h.A, [np.asarray(x, dtype=np.int64) for x in h.q], 0, 2)
+    return conv(gi), conv(gf)
+
+
+def cpu_sample_from_states(psi_samples, xi_samples, u):
+    """Times one forward Trotter step from each psi sample (slice index i -> i+1) and one backward step from each
+    xi sample (i -> i-1) plus the MPO overlaps with the oracle; returns (seconds per eval extrapolated, details)."""
+    from oracle import bh_mps as ob
+    D = CFG["d"] + 1
+    st = ob.BHStepper(CFG["L"], D, CFG["J"], CFG["tstep"], ob.TruncArgs(cutoff=CFG["cutoff"], maxm=CFG["maxm"]))
+    N = nt()
+    tf, tb, to = [], [], []
+    for (i, psi) in psi_samples:
+        p = psi.copy()
+        t0 = time.perf_counter()
+        st.step(p, u[i], u[i + 1], True)
+        tf.append(time.perf_counter() - t0)
+    for (i, xi) in xi_samples:
+        p = xi.copy()
+        t0 = time.perf_counter()
+        st.step(p, u[i], u[i - 1], False)
+        tb.append(time.perf_counter() - t0)
+    for (i, psi), (j, xi) in zip(psi_samples, xi_samples):
+        t0 = time.perf_counter()
+        ob.overlap_K(xi, psi)
+        to.append(time.perf_counter() - t0)
+    per_eval = (N - 1) * float(np.mean(tf)) + (N - 1) * float(np.mean(tb)) + (N + 1) * float(np.mean(to))
+    return per_eval, dict(fwd_step_s=float(np.mean(tf)), bwd_step_s=float(np.mean(tb)), overlap_s=float(np.mean(to)),
+                          cpu_seconds=float(np.sum(tf) + np.sum(tb) + np.sum(to)))
+
+
+def coarse_samples(u, npts, stride):
+    """Representative mid-ramp states for the CPU-only arm: the oracle itself evolves psi forward / xi backward with
+    `stride` Trotter steps merged into one (tstep*stride), and hands out the states at `npts` evenly spaced slices."""
+    from oracle import bh_mps as ob
+    D = CFG["d"] + 1
+    psi, xi = oracle_states()
+    N = nt()
+    coarse = ob.BHStepper(CFG["L"], D, CFG["J"], CFG["tstep"] * stride, ob.TruncArgs(cutoff=CFG["cutoff"], maxm=CFG["maxm"]))
+    want = sorted(set(int(round(x)) for x in np.linspace(stride, N - 1 - stride, npts)))
+    want = [w - w % stride for w in want]
+    ps, xs = [], []
+    i = 0
+    p = psi.copy()
+    while i + stride <= N - 1:
+        if i in want:
+            ps.append((i, p.copy()))
+        coarse.step(p, u[i], u[i + stride], True)
+        i += stride
+    j = N - 1
+    x = xi.copy()
+    wantb = [N - 1 - w for w in want]
+    while j - stride >= 0:
+        if j in wantb:
+            xs.append((j, x.copy()))
+        coarse.step(x, u[j], u[j - stride], False)
+        j -= stride
+    return ps, xs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncores = os.cpu_count() or 1
+    basis, c, u = make_problem_host(0)
+    t_prep0 = time.perf_counter()
+    ps, xs = coarse_samples(u, npts=6, stride=4)
+    prep = time.perf_counter() - t_prep0
+    vals, det = [], None
+    for k in range(args.warmup + args.steps):
+        per_eval, det = cpu_sample_from_states(ps, xs, u)
+        if k >= args.warmup:
+            vals.append(per_eval)
+    per_eval = float(np.mean(vals))
+    value = 1.0 / per_eval
+    sample = (f"oracle port (NumPy/OpenBLAS, {ncores} threads): 1 forward + 1 backward Trotter step and 1 MPO overlap at each of "
+              f"{len(ps)} evenly spaced ramp slices (states prepared by the oracle with 4 Trotter steps merged into one), "
+              f"extrapolated to 2*(Nt-1) steps + Nt+1 overlaps per eval; preparation {prep:.1f}s not timed")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per_eval * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "complex128 (f64)", "data": "synthetic",
+            "config": {"workload": "cfg2: BH L=20 Npart=20 d=5 T=2.0 tstep=0.01 GROUP M=10 chi=100 single cost+gradient eval", **CFG},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample, **det},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def fp64_peak_tflops(torch, dev):
+    """Measured FP64 GEMM peak of this GPU (cuBLAS DGEMM 4096^3, best of 5) -- the roofline denominator
+    (MEASURED_PEAKS.json has no FP64 figure)."""
+    n = 4096
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import optimalcontrolmps_b200 as oc
+    from optimalcontrolmps_b200.states import ground_state
+    from optimalcontrolmps_b200 import distributed as ocd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    ctx = oc.Context.default(local_rank)
+    lib = ctx.lib
+    L, d = CFG["L"], CFG["d"]
+    st = oc.BH_tDMRG(oc.BoseHubbard(L, d), CFG["J"], CFG["tstep"], oc.Args("Cutoff=", CFG["cutoff"], "Maxm=", CFG["maxm"]), ctx=ctx)
+    psi_i = ground_state(L, d, CFG["Npart"], CFG["U_i"])
+    psi_f = ground_state(L, d, CFG["Npart"], CFG["U_f"])
+    basis, c, u = make_problem_host(rank)          # every rank its own control (independent units)
+    ocp = oc.OptimalControl(psi_f, psi_i, st, basis, CFG["gamma"])
+    ocp.setThreadCount(2)                          # psi and xi sweeps on two streams (reference: 2 threads)
+    N, M = nt(), CFG["M"]
+
+    def one_eval():
+        g = ocp.getAnalyticGradient(list(c), True)         # host control in, host gradient out
+        cost = ocp.getCost(list(c), False)
+        return cost, g
+
+    for _ in range(args.warmup):
+        one_eval()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = lib.ocmps_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    res = None
+    for _ in range(args.steps):
+        res = one_eval()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
+    launches = lib.ocmps_launch_count() - l0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    # max over ranks of the device-timed region and of the end-to-end wall clock
+    tt = torch.tensor([dev_ms * 1e-3, wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        # one all-gather of the (cost, gradient) tuples -- the only collective of the batched-controls path
+        mine = np.concatenate([[res[0]], res[1]])
+        allres = ocd.allgather_array(mine, dev)
+    else:
+        allres = [np.concatenate([[res[0]], res[1]])]
+    t_dev, t_wall = float(tt[0]), float(tt[1])
+    value = world * args.steps / t_dev
+    e2e = world * args.steps / t_wall
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "complex128 (f64)", "data": "synthetic",
+            "config": {"workload": "cfg2: BH L=20 Npart=20 d=5 T=2.0 tstep=0.01 GROUP M=10 chi=100 single cost+gradient eval per GPU",
+                       **CFG, "Nt": N, "l2": "inputs larger than L2: the two slice stores are rewritten every eval (5.7 GB capacity)"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(8 * M + 8 * N), "d2h_bytes_per_step": int(8 * (1 + M) + 16 * 2 * N)},
+            "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "result": {"cost": float(allres[0][0]), "grad_norm": float(np.linalg.norm(allres[0][1:])),
+                       "max_bond_dim": int(ocp.psi_t.bond_dims().max())}}
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (block SVD), event-timed on its own streams in one extra eval ----
+        lib.ocmps_profile_enable(1)
+        one_eval()
+        out4 = np.zeros(4)
+        lib.ocmps_profile_read(out4.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_double)))
+        lib.ocmps_profile_enable(0)
+        peak = fp64_peak_tflops(torch, dev)
+        ms_tot, nl, fl_blk, fl_dense = out4
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        ach = fl_blk / (ms_tot * 1e-3) / 1e12 if ms_tot > 0 else 0.0
+        line["roofline"] = {"kernel": "jacobi_blocks_kernel (QR-preconditioned block Jacobi SVD)", "bound": "tensor",
+                            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
+                            "traffic": traffic, "launches": int(nl), "avg_launch_us": ms_tot * 1e3 / max(nl, 1),
+                            "share_of_two_stream_time": ms_tot / (2.0 * t_dev / args.steps * 1e3),
+                            "algorithmic_flops": "block-summed F_gram+F_evd = sum_q 8 n_q^2 m_q + 56/3 n_q^3 (SURVEY.md 8d)",
+                            "achieved_dense_formula": fl_dense / (ms_tot * 1e-3) / 1e12 if ms_tot > 0 else 0.0,
+                            "peak_source": "measured in this run: cuBLAS DGEMM 4096^3 burst (MEASURED_PEAKS.json has no FP64 figure)"}
+        if world == 1 and not args.no_cpu_baseline:
+            # ---- CPU baseline: the oracle port on this box's host cores, bounded sample taken at real slices ----
+            from oracle import bh_mps as ob
+            conv = lambda h: ob.MPS(h.A, [np.asarray(x, dtype=np.int64) for x in h.q], 0, 2)
+            idx = [int(round(x)) for x in np.linspace(4, N - 5, 8)]
+            ps = [(i, conv(ocp.psi_t.get(i).download())) for i in idx]
+            xs = [(i, conv(ocp.xi_t.get(i).download())) for i in idx]
+            per_eval, det = cpu_sample_from_states(ps, xs, u)
+            ncores = os.cpu_count() or 1
+            line["cpu_baseline"] = {"value": 1.0 / per_eval, "unit": UNIT, "cores": ncores, "kind": "port",
+                                    "sample": f"oracle port (NumPy/OpenBLAS, {ncores} threads): 1 forward + 1 backward Trotter step and 1 MPO "
+                                              f"overlap from each of 8 evenly spaced slices of this run's psi_t / xi_t, extrapolated to "
+                                              f"2*(Nt-1) steps + Nt+1 overlaps", **det}
+        if args.hessian_nt:
+            line["hessian"] = hessian_bench(args.hessian_nt, oc, ocd, st, psi_i, psi_f, world, dev, torch)
+        print(json.dumps(line), flush=True)
+    elif args.hessian_nt:
+        hessian_bench(args.hessian_nt, oc, ocd, st, psi_i, psi_f, world, dev, torch)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def hessian_bench(Nt, oc, ocd, st, psi_i, psi_f, world, dev, torch):
+    """GRAPE Hessian of a horizon of Nt points with rows sharded over the ranks (cfg3 shape when Nt=201)."""
+    import torch.distributed as dist
+    u = list(np.linspace(CFG["U_i"], 30.0, Nt))
+    och = oc.OptimalControl(psi_f, psi_i, st, Nt, CFG["gamma"])
+    och.setThreadCount(4)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    if world > 1:
+        H = ocd.sharded_hessian(och, u, True, dev)
+    else:
+        H = np.array(och.getHessian(u, True))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    return {"Nt": Nt, "wall_s": dt, "n_gpus": world, "checksum": float(np.abs(H).sum())}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--hessian-nt", type=int, default=0, help="additionally time a sharded GRAPE Hessian with this many time points")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -43,6 +43,10 @@ const char* ocmps_last_error(void);
 int ocmps_version(void);
 /* number of CUDA kernels launched by this library so far (bench.py reports it as gpu_launches) */
 long long ocmps_launch_count(void);
+/* measurement aid (bench.py): CUDA-event timing of the dominant kernel (the block SVD) on its own stream.
+ * read -> out4 = { total ms inside the kernel, launches, block-summed algorithmic flops, dense-formula flops } */
+int ocmps_profile_enable(int on);
+int ocmps_profile_read(double* out4);
 
 /* ---- context ---- */
 int ocmps_ctx_create(int device, ocmps_ctx** out);

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libocmps.so")
 
 # every symbol include/ocmps.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    "ocmps_last_error", "ocmps_version", "ocmps_launch_count",
+    "ocmps_last_error", "ocmps_version", "ocmps_launch_count", "ocmps_profile_enable", "ocmps_profile_read",
     "ocmps_ctx_create", "ocmps_ctx_destroy", "ocmps_ctx_synchronize",
     "ocmps_mps_create", "ocmps_mps_destroy", "ocmps_mps_upload", "ocmps_mps_sizes", "ocmps_mps_download",
     "ocmps_mps_bond_dims", "ocmps_mps_copy", "ocmps_mps_norm", "ocmps_overlap", "ocmps_overlap_K",
@@ -47,6 +47,8 @@ def load():
         "ocmps_last_error": (C.c_char_p, []),
         "ocmps_version": (i, []),
         "ocmps_launch_count": (C.c_longlong, []),
+        "ocmps_profile_enable": (i, [i]),
+        "ocmps_profile_read": (i, [pd]),
         "ocmps_ctx_create": (i, [i, pvp]),
         "ocmps_ctx_destroy": (i, [vp]),
         "ocmps_ctx_synchronize": (i, [vp]),

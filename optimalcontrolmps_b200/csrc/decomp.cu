@@ -16,7 +16,8 @@
 // One CTA per block.
 #include "ocmps_internal.h"
 
-__device__ unsigned long long g_jac_dbg[8];   // [0] sum of sweeps, [1] blocks, [2] max sweeps, [3] sweeps of blocks with nv>=64, [4] such blocks
+__device__ unsigned long long g_jac_dbg[8];
+__device__ double g_jac_flops[2];             // algorithmic flops of the decompositions: [0] block-summed, [1] dense formula   // [0] sum of sweeps, [1] blocks, [2] max sweeps, [3] sweeps of blocks with nv>=64, [4] such blocks
 
 namespace {
 
@@ -344,7 +345,16 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
     __syncthreads();
     if (!converged && sweep == JAC_MAX_SWEEPS - 1 && tid == 0) atomicOr(b.status, OCMPS_ST_NOCONV);
   }
-  if (tid == 0) atomicAdd(&g_jac_dbg[1], 1ull);
+  if (tid == 0) {
+    atomicAdd(&g_jac_dbg[1], 1ull);
+    // F_gram = 8 n^2 m, F_evd = 56/3 n^3 with n the side that is orthogonalised (here per charge block)
+    const double nn = (double)len, mm = (double)nv;
+    atomicAdd(&g_jac_flops[0], 8.0 * nn * nn * mm + (56.0 / 3.0) * nn * nn * nn);
+    if (blockIdx.x == 0) {
+      const double dn = mode == 0 ? (double)w->n : (double)w->m, dm = mode == 0 ? (double)w->m : (double)w->n;
+      atomicAdd(&g_jac_flops[1], 8.0 * dn * dn * dm + (56.0 / 3.0) * dn * dn * dn);
+    }
+  }
 
   // ---- phase 4: spectrum + normalised right vectors Z[j][physical vector] ----
   __syncthreads();
@@ -628,8 +638,45 @@ void launch_decomp_setup(const DecompArgs& a, const DecompBuffers& b, cudaStream
   decomp_setup_kernel<<<1, OCMPS_MAX_Q, 0, s>>>(a, b);
 }
 
+#include <vector>
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static size_t g_prof_used = 0;
+
+void profile_enable(bool on) {
+  g_prof_on = on;
+  g_prof_used = 0;
+  double z[2] = {0.0, 0.0};
+  cudaMemcpyToSymbol(g_jac_flops, z, sizeof(z));
+}
+// out: [0] total ms inside the block-SVD kernel, [1] launches, [2] block-summed algorithmic flops, [3] dense-formula flops
+void profile_read(double* out) {
+  cudaDeviceSynchronize();
+  double ms = 0.0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, g_prof_events[i].first, g_prof_events[i].second);
+    ms += t;
+  }
+  double fl[2];
+  cudaMemcpyFromSymbol(fl, g_jac_flops, sizeof(fl));
+  out[0] = ms; out[1] = (double)g_prof_used; out[2] = fl[0]; out[3] = fl[1];
+}
+
 void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_launch, size_t smem_limit, bool need_global,
                           double rank_tol, cudaStream_t s) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_prof_on) {
+    if (g_prof_used == g_prof_events.size()) {
+      cudaEvent_t x, y;
+      cudaEventCreate(&x); cudaEventCreate(&y);
+      g_prof_events.push_back({x, y});
+    }
+    e0 = g_prof_events[g_prof_used].first; e1 = g_prof_events[g_prof_used].second;
+    ++g_prof_used;
+    cudaEventRecord(e0, s);
+  }
+  struct Tail { cudaEvent_t e; cudaStream_t s; ~Tail() { if (e) cudaEventRecord(e, s); } } tail{e1, s};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !g_jac_attr_set[dev]) {

@@ -656,6 +656,8 @@ extern "C" {
 const char* ocmps_last_error(void) { return g_err.c_str(); }
 int ocmps_version(void) { return 100; }
 long long ocmps_launch_count(void) { return g_ocmps_launches; }
+int ocmps_profile_enable(int on) { profile_enable(on != 0); return OCMPS_OK; }
+int ocmps_profile_read(double* out4) { if (!out4) return fail(OCMPS_ERR_INVALID, "null argument"); profile_read(out4); return OCMPS_OK; }
 
 int ocmps_ctx_create(int device, ocmps_ctx** out) {
   if (!out) return fail(OCMPS_ERR_INVALID, "null out");

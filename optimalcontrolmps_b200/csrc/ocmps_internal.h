@@ -63,6 +63,8 @@ struct Phases { double re[4][OCMPS_MAX_D]; double im[4][OCMPS_MAX_D]; };
 extern long long g_ocmps_launches;   // kernels launched so far (bench.py reports it)
 
 void debug_jacobi_counters(unsigned long long* out, bool reset);
+void profile_enable(bool on);
+void profile_read(double* out);
 
 // ---- kernels (launchers) ----
 void launch_zgemm(const GemmDesc* d_descs, int batch, int maxM, int maxN, cudaStream_t s);
