@@ -50,75 +50,119 @@ __device__ __forceinline__ int col_charge(const DecompArgs& a, int j, int chiR) 
   return (a.kind == DK_ORTH_LEFT) ? a.qR[j] : a.qR[j % chiR] - j / chiR;
 }
 
-// comp_blk / comp_rank live behind comp_idx in the same allocation (see engine: 3 * NV_MAX ints)
-__global__ void __launch_bounds__(OCMPS_MAX_Q) decomp_setup_kernel(DecompArgs a, DecompBuffers b) {
+// Block table and index lists of one decomposition.  Bond charges are kept sorted ascending by the engine
+// (upload sorts, truncation emits sorted labels), so the members of a charge bin are a handful of contiguous
+// index ranges and every list entry can be placed independently: rank within the bin = (ranges of smaller s)
+// + offset inside its own range.  comp_blk / comp_rank live behind comp_idx, vec_blk / vec_rank behind vec_idx
+// (3 * NV_MAX ints each).
+constexpr int SETUP_THREADS = 1024;
+constexpr int QT = OCMPS_MAX_Q + 2 * OCMPS_MAX_D + 2;     // charge tables with room for q +- s
+
+__global__ void __launch_bounds__(SETUP_THREADS) decomp_setup_kernel(DecompArgs a, DecompBuffers b) {
+  __shared__ int startL[QT + 1], startR[QT + 1];          // first bond index with charge >= c (c shifted by OCMPS_MAX_D)
   __shared__ int cnt_v[OCMPS_MAX_Q], cnt_c[OCMPS_MAX_Q], off_v[OCMPS_MAX_Q], off_c[OCMPS_MAX_Q], blk_of_q[OCMPS_MAX_Q];
-  __shared__ short s_rq[NV_MAX], s_cq[NV_MAX];      // charges of rows / columns (-1: outside [0, MAX_Q))
   __shared__ int s_bad;
-  const int chiL = *a.dimL, chiR = *a.dimR;
+  const int chiL = *a.dimL, chiR = *a.dimR, D = a.D;
   const Geometry g = geometry(a, chiL, chiR);
-  const int q = threadIdx.x;
-  const int ncomp = g.mode == 0 ? g.n : g.m;
+  const int tid = threadIdx.x;
+  const int Drow = (a.kind == DK_ORTH_RIGHT) ? 1 : D;     // rows are (l, t): charge qL[l] + t
+  const int Dcol = (a.kind == DK_ORTH_LEFT) ? 1 : D;      // cols are (t, r): charge qR[r] - t
   int* comp_blk = b.comp_idx + NV_MAX;
   int* comp_rank = b.comp_idx + 2 * NV_MAX;
   int* vec_blk = b.vec_idx + NV_MAX;
   int* vec_rank = b.vec_idx + 2 * NV_MAX;
-  if (q == 0) s_bad = 0;
+  const int SH = OCMPS_MAX_D;                             // table shift so that q - t >= -D is addressable
+  if (tid == 0) s_bad = 0;
   __syncthreads();
-  for (int i = q; i < g.n; i += blockDim.x) {
-    int c = row_charge(a, i);
-    if (c >= OCMPS_MAX_Q) { s_bad = 1; c = -1; }
-    s_rq[i] = (short)(c < 0 ? -1 : c);
+  // start tables from the sorted labels: startX[c + SH] = first index whose charge is >= c
+  for (int i = tid; i <= chiL; i += SETUP_THREADS) {
+    const int lo = (i == 0) ? -SH : a.qL[i - 1] + 1;
+    const int hi = (i == chiL) ? QT - SH : a.qL[i];
+    if (i < chiL && (hi < 0 || hi >= OCMPS_MAX_Q || hi + 1 < lo)) s_bad = 1;       // out of range or not sorted
+    for (int c = lo; c <= hi && c + SH <= QT; ++c) startL[c + SH] = i;
   }
-  for (int j = q; j < g.m; j += blockDim.x) {
-    int c = col_charge(a, j, chiR);
-    if (c >= OCMPS_MAX_Q) { s_bad = 1; c = -1; }
-    s_cq[j] = (short)(c < 0 ? -1 : c);
+  for (int i = tid; i <= chiR; i += SETUP_THREADS) {
+    const int lo = (i == 0) ? -SH : a.qR[i - 1] + 1;
+    const int hi = (i == chiR) ? QT - SH : a.qR[i];
+    if (i < chiR && (hi < 0 || hi >= OCMPS_MAX_Q || hi + 1 < lo)) s_bad = 1;
+    for (int c = lo; c <= hi && c + SH <= QT; ++c) startR[c + SH] = i;
   }
-  for (int i = q; i < ncomp; i += blockDim.x) { comp_blk[i] = -1; comp_rank[i] = 0; }
-  for (int i = q; i < (g.mode == 0 ? g.m : g.n); i += blockDim.x) { vec_blk[i] = -1; vec_rank[i] = 0; }
   __syncthreads();
-  const short* vq = g.mode == 0 ? s_cq : s_rq;      // vectors: columns (mode 0) or rows (mode 1)
-  const short* cq = g.mode == 0 ? s_rq : s_cq;
-  const int nvec = g.mode == 0 ? g.m : g.n;
-  int cv = 0, cc = 0;
-  for (int i = 0; i < nvec; ++i) cv += (vq[i] == q);
-  for (int i = 0; i < ncomp; ++i) cc += (cq[i] == q);
-  cnt_v[q] = cv; cnt_c[q] = cc;
-  if (s_bad && q == 0) atomicOr(b.status, OCMPS_ST_CHARGE);
+  if (s_bad) { if (tid == 0) atomicOr(b.status, OCMPS_ST_CHARGE); }
+#define CNTL(c) (((c) + SH < 0 || (c) + SH >= QT) ? 0 : startL[(c) + SH + 1] - startL[(c) + SH])
+#define CNTR(c) (((c) + SH < 0 || (c) + SH >= QT) ? 0 : startR[(c) + SH + 1] - startR[(c) + SH])
+  if (tid < OCMPS_MAX_Q) {
+    const int q = tid;
+    int nr = 0, nc = 0;
+    for (int t = 0; t < Drow; ++t) nr += CNTL(q - t);
+    for (int t = 0; t < Dcol; ++t) nc += CNTR(q + t);
+    cnt_v[q] = g.mode == 0 ? nc : nr;
+    cnt_c[q] = g.mode == 0 ? nr : nc;
+  }
   __syncthreads();
-  if (q == 0) {
+  if (tid == 0) {
     DecompWork* w = b.dw;
     int nb = 0, ov = 0, oc = 0, ows = 0;
     for (int c = 0; c < OCMPS_MAX_Q; ++c) {
-      blk_of_q[c] = -1;
+      int bid = -1;
       if (cnt_v[c] > 0 && cnt_c[c] > 0) {
         if (nb < OCMPS_MAX_BLK) {
-          DecompBlock& B = w->blk[nb];
-          B.q = c; B.nv = cnt_v[c]; B.len = cnt_c[c];
-          B.vec_off = ov; B.comp_off = oc; B.ws_off = ows; B.p_off = ov;
-          blk_of_q[c] = nb;
+          bid = nb;
           off_v[c] = ov; off_c[c] = oc;
+          DecompBlock B;
+          B.q = c; B.nv = cnt_v[c]; B.len = cnt_c[c];
+          B.vec_off = ov; B.comp_off = oc; B.ws_off = ows; B.p_off = ov; B.pad = 0;
+          w->blk[nb] = B;
           ov += cnt_v[c]; oc += cnt_c[c]; ows += cnt_v[c] * cnt_c[c];
           ++nb;
         } else {
           atomicOr(b.status, OCMPS_ST_TOOMANYBLK);
         }
       }
+      blk_of_q[c] = bid;
     }
     w->n = g.n; w->m = g.m; w->ld = g.m; w->mode = g.mode;
     w->nblocks = nb; w->nvtot = ov; w->newdim = 0; w->scale = 1.0;
   }
   __syncthreads();
-  const int mb = blk_of_q[q];
-  if (mb >= 0) {
-    const int ov = off_v[q], oc = off_c[q];
-    int kv = 0, kc = 0;
-    for (int i = 0; i < nvec; ++i)
-      if (vq[i] == q) { b.vec_idx[ov + kv] = i; b.vecq[ov + kv] = q; vec_blk[i] = mb; vec_rank[i] = kv; ++kv; }
-    for (int i = 0; i < ncomp; ++i)
-      if (cq[i] == q) { b.comp_idx[oc + kc] = i; comp_blk[i] = mb; comp_rank[i] = kc; ++kc; }
+  // rows: index i = l * Drow + t
+  for (int i = tid; i < g.n; i += SETUP_THREADS) {
+    const int l = i / Drow, t = i % Drow;
+    const int q = a.qL[l] + t;
+    int bid = -1, rank = 0;
+    if (q >= 0 && q < OCMPS_MAX_Q) {
+      bid = blk_of_q[q];
+      for (int tt = 0; tt < t; ++tt) rank += CNTL(q - tt);
+      rank += l - startL[q - t + SH];
+    }
+    if (g.mode == 0) {                                   // rows are components
+      comp_blk[i] = bid; comp_rank[i] = rank;
+      if (bid >= 0) b.comp_idx[off_c[q] + rank] = i;
+    } else {                                             // rows are vectors
+      vec_blk[i] = bid; vec_rank[i] = rank;
+      if (bid >= 0) { b.vec_idx[off_v[q] + rank] = i; b.vecq[off_v[q] + rank] = q; }
+    }
   }
+  // cols: index j = t * chiR + r
+  for (int j = tid; j < g.m; j += SETUP_THREADS) {
+    const int t = (Dcol == 1) ? 0 : j / chiR, r = (Dcol == 1) ? j : j % chiR;
+    const int q = a.qR[r] - t;
+    int bid = -1, rank = 0;
+    if (q >= 0 && q < OCMPS_MAX_Q) {
+      bid = blk_of_q[q];
+      for (int tt = 0; tt < t; ++tt) rank += CNTR(q + tt);
+      rank += r - startR[q + t + SH];
+    }
+    if (g.mode == 0) {                                   // cols are vectors
+      vec_blk[j] = bid; vec_rank[j] = rank;
+      if (bid >= 0) { b.vec_idx[off_v[q] + rank] = j; b.vecq[off_v[q] + rank] = q; }
+    } else {
+      comp_blk[j] = bid; comp_rank[j] = rank;
+      if (bid >= 0) b.comp_idx[off_c[q] + rank] = j;
+    }
+  }
+#undef CNTL
+#undef CNTR
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -162,6 +206,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   const int* vidx = b.vec_idx + B.vec_off;
   const int* cidx = b.comp_idx + B.comp_off;
 
+  const long long t_start = clock64();
   // ---- phase 0: gather the block, Y[v][c] = component c of vector v ----
   if (mode == 0) {   // vectors are columns of X: consecutive threads take consecutive vectors (coalesced over columns)
     for (int e = tid; e < nv * len; e += JAC_THREADS) {
@@ -193,6 +238,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   const double F = s_F;
   const double rtol_abs = F * rank_tol;
 
+  const long long t_qr0 = clock64();
   // ---- phase 1: Householder QR with column pivoting, in place; R's strict upper part and rdiag remain ----
   const int kmax = nv < len ? nv : len;
   int keff = 0;
@@ -275,6 +321,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
     __syncthreads();
   }
 
+  const long long t_jac0 = clock64();
   // ---- phase 3: one-sided Jacobi on the keff rows of R (length nv each) ----
   const int npad = (keff + 1) & ~1;
   const int npairs = npad / 2;
@@ -358,6 +405,12 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
 
   // ---- phase 4: spectrum + normalised right vectors Z[j][physical vector] ----
   __syncthreads();
+  const long long t_jac1 = clock64();
+  if (tid == 0 && nv >= 64) {
+    atomicAdd(&g_jac_dbg[5], (unsigned long long)(t_jac0 - t_qr0));
+    atomicAdd(&g_jac_dbg[6], (unsigned long long)(t_jac1 - t_jac0));
+    atomicAdd(&g_jac_dbg[7], (unsigned long long)(t_jac1 - t_start));
+  }
   for (int v = warp; v < nv; v += nwarps) {
     if (v < keff) {
       const cplx* y = Z + v * nv;
@@ -635,7 +688,7 @@ void debug_jacobi_counters(unsigned long long* out, bool reset) {
 }
 
 void launch_decomp_setup(const DecompArgs& a, const DecompBuffers& b, cudaStream_t s) {
-  decomp_setup_kernel<<<1, OCMPS_MAX_Q, 0, s>>>(a, b);
+  decomp_setup_kernel<<<1, SETUP_THREADS, 0, s>>>(a, b);
 }
 
 #include <vector>

@@ -715,18 +715,41 @@ int ocmps_mps_upload(ocmps_mps* m, const int* bond_dims, const int* charges, con
       return fail(OCMPS_ERR_CAPACITY, "upload: bond dimension " + std::to_string(bond_dims[b]) + " at bond " + std::to_string(b) +
                                           " exceeds capacity " + std::to_string(lay.capb[b]));
   if (bond_dims[0] != 1 || bond_dims[lay.L] != 1) return fail(OCMPS_ERR_INVALID, "upload: boundary bonds must have dimension 1");
-  size_t off = 0, qoff = 0;
+  // The engine keeps bond charges sorted ascending (the block bookkeeping relies on it); a permutation of a
+  // bond index is a gauge choice, so unsorted labels are sorted here, stably, together with the tensors.
+  std::vector<std::vector<int>> perm(lay.L + 1);
+  {
+    size_t qo = 0;
+    for (int b = 0; b <= lay.L; ++b) {
+      const int nb = bond_dims[b];
+      for (int i = 0; i < nb; ++i)
+        if (charges[qo + i] < 0 || charges[qo + i] >= OCMPS_MAX_Q) return fail(OCMPS_ERR_INVALID, "upload: charge outside [0,256)");
+      perm[b].resize(nb);
+      for (int i = 0; i < nb; ++i) perm[b][i] = i;
+      const int* qb = charges + qo;
+      std::stable_sort(perm[b].begin(), perm[b].end(), [qb](int x, int y) { return qb[x] < qb[y]; });
+      std::vector<int> sorted(nb);
+      for (int i = 0; i < nb; ++i) sorted[i] = qb[perm[b][i]];
+      CK(cudaMemcpy(m->q(b), sorted.data(), sizeof(int) * nb, cudaMemcpyHostToDevice));
+      qo += nb;
+    }
+  }
+  size_t off = 0;
+  std::vector<zc> tmp;
+  const zc* src = reinterpret_cast<const zc*>(tensors);
   for (int j = 0; j < lay.L; ++j) {
     m->cur[j] = 0;
-    size_t n = (size_t)bond_dims[j] * lay.D * bond_dims[j + 1];
-    CK(cudaMemcpy(m->site(j), tensors + 2 * off, sizeof(cplx) * n, cudaMemcpyHostToDevice));
+    const int cl = bond_dims[j], cr = bond_dims[j + 1], D = lay.D;
+    const size_t n = (size_t)cl * D * cr;
+    tmp.resize(n);
+    for (int l = 0; l < cl; ++l)
+      for (int sI = 0; sI < D; ++sI) {
+        const zc* in = src + off + ((size_t)perm[j][l] * D + sI) * cr;
+        zc* out = tmp.data() + ((size_t)l * D + sI) * cr;
+        for (int r = 0; r < cr; ++r) out[r] = in[perm[j + 1][r]];
+      }
+    CK(cudaMemcpy(m->site(j), tmp.data(), sizeof(cplx) * n, cudaMemcpyHostToDevice));
     off += n;
-  }
-  for (int b = 0; b <= lay.L; ++b) {
-    for (int i = 0; i < bond_dims[b]; ++i)
-      if (charges[qoff + i] < 0 || charges[qoff + i] >= OCMPS_MAX_Q) return fail(OCMPS_ERR_INVALID, "upload: charge outside [0,256)");
-    CK(cudaMemcpy(m->q(b), charges + qoff, sizeof(int) * bond_dims[b], cudaMemcpyHostToDevice));
-    qoff += bond_dims[b];
   }
   CK(cudaMemcpy(m->d_dims, bond_dims, sizeof(int) * (lay.L + 1), cudaMemcpyHostToDevice));
   m->llim = llim; m->rlim = rlim;

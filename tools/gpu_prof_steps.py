@@ -29,5 +29,5 @@ c2 = lib.ocmps_launch_count()
 import ctypes
 dbg=(ctypes.c_ulonglong*8)()
 lib.ocmps_debug_jacobi(dbg,0)
-print("jacobi dbg: sweeps",dbg[0],"blocks",dbg[1],"max sweeps",dbg[2],"big-block sweeps",dbg[3],"big blocks",dbg[4])
+print("jacobi dbg: sweeps",dbg[0],"blocks",dbg[1],"max sweeps",dbg[2],"big-block sweeps",dbg[3],"big blocks",dbg[4], "per big block: QR kclk",dbg[5]/max(dbg[4],1)/1e3,"Jacobi kclk",dbg[6]/max(dbg[4],1)/1e3,"total kclk",dbg[7]/max(dbg[4],1)/1e3)
 print("warm launches", c1 - c0, "prof launches", c2 - c1, "per step ms", (t1 - t0) / nprof * 1e3, pd.bond_dims())
