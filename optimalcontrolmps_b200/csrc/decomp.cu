@@ -21,7 +21,8 @@ __device__ double g_jac_flops[2];             // algorithmic flops of the decomp
 
 namespace {
 
-constexpr int JAC_THREADS = 1024;
+constexpr int JAC_THREADS = 512;
+constexpr int JAC_EPL = 8;                // elements per lane cached in registers (rows up to 16*8 = 128 long)
 constexpr int JAC_NV_SMEM = 512;          // cached norms in shared memory for blocks with at most this many vectors
 constexpr int JAC_MAX_SWEEPS = 60;
 constexpr double JAC_TOL2 = 1e-28;        // rotate while |<p|q>|^2 > tol^2 <p|p><q|q>, tol = 1e-14
@@ -182,7 +183,7 @@ __device__ __forceinline__ double half_sum(double v) {
 template <bool SMEM>
 __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a, DecompBuffers b, int smem_elems, double rank_tol) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_rot, s_keff;
+  __shared__ int s_rot, s_keff, s_big;
   __shared__ double s_F;
   __shared__ double s_nrm[JAC_NV_SMEM];
   __shared__ double s_rdr[JAC_NV_SMEM], s_rdi[JAC_NV_SMEM];   // diagonal of R
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   const int npad = (keff + 1) & ~1;
   const int npairs = npad / 2;
   const double thr = F * DEFLATE_REL;
+  const bool cached = nv <= 16 * JAC_EPL;
   bool converged = false;
   for (int sweep = 0; sweep < JAC_MAX_SWEEPS && !converged; ++sweep) {
     for (int v = warp; v < keff; v += nwarps) {        // exact Gram diagonal at the start of every sweep
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
       s = warp_sum(s);
       if (lane == 0) nrm[v] = s;
     }
-    if (tid == 0) s_rot = 0;
+    if (tid == 0) { s_rot = 0; s_big = 0; }
     __syncthreads();
     if (keff < 2) break;
     for (int r = 0; r < npad - 1; ++r) {
@@ -348,11 +350,24 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
         cplx* yp = Z + (act ? p : 0) * nv;
         cplx* yq = Z + (act ? q : 0) * nv;
         double cre = 0.0, cim = 0.0;
+        cplx ru[JAC_EPL], rv[JAC_EPL];                 // the pair's elements stay in registers between dot and update
         if (act) {
-          for (int c = hl; c < nv; c += 16) {
-            cplx u = yp[c], v = yq[c];
-            cre += u.x * v.x + u.y * v.y;      // conj(u) * v
-            cim += u.x * v.y - u.y * v.x;
+          if (cached) {
+#pragma unroll
+            for (int e = 0; e < JAC_EPL; ++e) {
+              const int c = hl + 16 * e;
+              if (c < nv) {
+                ru[e] = yp[c]; rv[e] = yq[c];
+                cre += ru[e].x * rv[e].x + ru[e].y * rv[e].y;      // conj(u) * v
+                cim += ru[e].x * rv[e].y - ru[e].y * rv[e].x;
+              }
+            }
+          } else {
+            for (int c = hl; c < nv; c += 16) {
+              cplx u = yp[c], v = yq[c];
+              cre += u.x * v.x + u.y * v.y;
+              cim += u.x * v.y - u.y * v.x;
+            }
           }
         }
         cre = half_sum(cre); cim = half_sum(cim);
@@ -363,31 +378,50 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
           if (aa <= thr && aa > 0.0) { for (int c = hl; c < nv; c += 16) yp[c] = make_double2(0.0, 0.0); if (hl == 0) nrm[p] = 0.0; }
           if (bb <= thr && bb > 0.0) { for (int c = hl; c < nv; c += 16) yq[c] = make_double2(0.0, 0.0); if (hl == 0) nrm[q] = 0.0; }
         } else if (c2 > JAC_TOL2 * aa * bb) {
+          // rotation angle theta: tan 2theta = |c| / d, d = (b - a)/2.  Two reciprocal square roots give
+          // cos and sin without a division: cos^2 = (1 + |cos 2theta|)/2, sin = sin 2theta / (2 cos).
           const double inv_r = rsqrt(c2);
           const double rr = c2 * inv_r;                         // |c|
           const double dd = 0.5 * (bb - aa);
-          const double hh = sqrt(dd * dd + c2);
-          const double tt = (dd >= 0.0 ? rr : -rr) / (fabs(dd) + hh);   // tan of the rotation angle
-          const double cs = rsqrt(1.0 + tt * tt);
-          const double sn = cs * tt;
+          const double ih = rsqrt(dd * dd + c2);
+          const double cs2 = 0.5 + 0.5 * fabs(dd) * ih;
+          const double ics = rsqrt(cs2);
+          const double cs = cs2 * ics;
+          const double snm = 0.5 * rr * ih * ics;
+          const double sn = dd >= 0.0 ? snm : -snm;
           const double phr = cre * inv_r, phi = cim * inv_r;    // e^{i phi} = c / |c|, absorbed into vector q
-          for (int c = hl; c < nv; c += 16) {
-            const cplx u = yp[c], v = yq[c];
-            const double vx = phr * v.x + phi * v.y, vy = phr * v.y - phi * v.x;
-            yp[c] = make_double2(cs * u.x - sn * vx, cs * u.y - sn * vy);
-            yq[c] = make_double2(sn * u.x + cs * vx, sn * u.y + cs * vy);
+          if (cached) {
+#pragma unroll
+            for (int e = 0; e < JAC_EPL; ++e) {
+              const int c = hl + 16 * e;
+              if (c < nv) {
+                const double vx = phr * rv[e].x + phi * rv[e].y, vy = phr * rv[e].y - phi * rv[e].x;
+                yp[c] = make_double2(cs * ru[e].x - sn * vx, cs * ru[e].y - sn * vy);
+                yq[c] = make_double2(sn * ru[e].x + cs * vx, sn * ru[e].y + cs * vy);
+              }
+            }
+          } else {
+            for (int c = hl; c < nv; c += 16) {
+              const cplx u = yp[c], v = yq[c];
+              const double vx = phr * v.x + phi * v.y, vy = phr * v.y - phi * v.x;
+              yp[c] = make_double2(cs * u.x - sn * vx, cs * u.y - sn * vy);
+              yq[c] = make_double2(sn * u.x + cs * vx, sn * u.y + cs * vy);
+            }
           }
           if (hl == 0) {
-            const double na = aa - tt * rr, nb = bb + tt * rr;
+            const double trr = sn * ics * rr;                   // tan(theta) |c|
+            const double na = aa - trr, nb = bb + trr;
             nrm[p] = na > 0.0 ? na : 0.0;
             nrm[q] = nb > 0.0 ? nb : 0.0;
             s_rot = 1;
+            if (c2 > 1e-16 * aa * bb) s_big = 1;                // an off-diagonal above 1e-8 (relative) was seen
           }
         }
       }
       __syncthreads();
     }
-    converged = (s_rot == 0);
+    // quadratic convergence: if every rotated pair had |<p|q>| < 1e-8 |p||q|, the residuals are now ~1e-16
+    converged = (s_rot == 0) || (s_big == 0);
     if (tid == 0) { atomicAdd(&g_jac_dbg[0], 1ull); atomicMax(&g_jac_dbg[2], (unsigned long long)(sweep + 1)); if (nv >= 64) atomicAdd(&g_jac_dbg[3], 1ull); if (nv >= 64 && sweep == 0) atomicAdd(&g_jac_dbg[4], 1ull); }
     __syncthreads();
     if (!converged && sweep == JAC_MAX_SWEEPS - 1 && tid == 0) atomicOr(b.status, OCMPS_ST_NOCONV);
