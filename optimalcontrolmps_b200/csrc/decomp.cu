@@ -472,6 +472,7 @@ __global__ void __launch_bounds__(1024) truncate_kernel(DecompArgs a, DecompBuff
   __shared__ double sSorted[NV_MAX];
   __shared__ short sQ[NV_MAX];
   __shared__ unsigned char sKeep[NV_MAX];
+  __shared__ short sPos[NV_MAX];
   __shared__ double s_docut;
   __shared__ int s_total;
   DecompWork* w = b.dw;
@@ -551,7 +552,9 @@ __global__ void __launch_bounds__(1024) truncate_kernel(DecompArgs a, DecompBuff
       }
     }
     b.pos[i] = pos;
+    sPos[i] = (short)pos;
   }
+  __syncthreads();
   if (tid == 0) {
     int k = total;
     if (k > tp.cap) { atomicOr(b.status, OCMPS_ST_CAPACITY); k = tp.cap; }
@@ -559,7 +562,7 @@ __global__ void __launch_bounds__(1024) truncate_kernel(DecompArgs a, DecompBuff
     *a.dimNew = k;
     // Frobenius norm of the tensor that carries the centre = sqrt(sum of kept weights), fixed summation order
     double kept = 0.0;
-    for (int i = 0; i < nv; ++i) if (sKeep[i] && b.pos[i] < tp.cap) kept += sP[i];
+    for (int i = 0; i < nv; ++i) if (sKeep[i] && sPos[i] < tp.cap) kept += sP[i];
     double scale = 1.0;
     if (tp.normalize) {
       const double nrm = sqrt(kept);
@@ -617,25 +620,33 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_factors_kernel(DecompArgs
   for (int v = tid; v < nv; v += BUILD_THREADS) zs[v] = Zj[v];
   __syncthreads();
   double part = 0.0;
-  for (int c = tid; c < len; c += BUILD_THREADS) {
-    double sr = 0.0, si = 0.0;
-    if (mode == 0) {
+  if (mode == 0) {
+    // vectors are columns of X: one warp per output component, lanes stride over the (nearly contiguous) columns
+    const int lane = tid & 31, wp = tid >> 5;
+    for (int c = wp; c < len; c += BUILD_THREADS / 32) {
       const cplx* row = a.X + (size_t)cidx[c] * ld;
-      for (int v = 0; v < nv; ++v) {
+      double sr = 0.0, si = 0.0;
+      for (int v = lane; v < nv; v += 32) {
         const cplx x = row[vidx[v]], z = zs[v];
         sr += x.x * z.x + x.y * z.y;          // x * conj(z)
         si += x.y * z.x - x.x * z.y;
       }
-    } else {
+      sr = warp_sum(sr); si = warp_sum(si);
+      if (lane == 0) { out[c] = make_double2(sr, si); part += sr * sr + si * si; }
+    }
+  } else {
+    // vectors are rows of X: one thread per output component, consecutive threads read consecutive columns
+    for (int c = tid; c < len; c += BUILD_THREADS) {
       const int col = cidx[c];
+      double sr = 0.0, si = 0.0;
       for (int v = 0; v < nv; ++v) {
         const cplx x = a.X[(size_t)vidx[v] * ld + col], z = zs[v];
         sr += x.x * z.x + x.y * z.y;
         si += x.y * z.x - x.x * z.y;
       }
+      out[c] = make_double2(sr, si);
+      part += sr * sr + si * si;
     }
-    out[c] = make_double2(sr, si);
-    part += sr * sr + si * si;
   }
   part = warp_sum(part);
   if ((tid & 31) == 0) red[tid >> 5] = part;

@@ -23,9 +23,12 @@ __global__ void merge_setup_kernel(GemmDesc* d, const cplx* A1, const cplx* A2, 
 }
 
 // theta'[l,t1,t2,r] = o1[t1] o2[t2] sum_{s1,s2} G[(t1,t2),(s1,s2)] i1[s1] i2[s2] theta[l,s1,s2,r]
-// (src/BH_tDMRG.cpp:150-159).  One thread per (l, r); the D^2 x D^2 gate sits in shared memory.
+// (src/BH_tDMRG.cpp:150-159).  One thread per (l, r).  The gate conserves the boson number and theta[l,.,.,r]
+// lives in the single sector s1 + s2 = qR[r] - qL[l], so only a (<= D) x (<= D) sub-block of the D^2 x D^2 gate
+// acts: at most D inputs, D outputs, D^2 complex multiply-adds per thread instead of D^4.
 template <int D>
 __global__ void __launch_bounds__(128) gate_apply_kernel(cplx* __restrict__ theta, const int* dimL, const int* dimR,
+                                                        const int* __restrict__ qL, const int* __restrict__ qR,
                                                         const cplx* __restrict__ G, Phases ph) {
   extern __shared__ __align__(16) unsigned char gate_smem[];
   cplx* W = reinterpret_cast<cplx*>(gate_smem);
@@ -33,7 +36,6 @@ __global__ void __launch_bounds__(128) gate_apply_kernel(cplx* __restrict__ thet
   for (int e = threadIdx.x; e < D * D * D * D; e += blockDim.x) {
     const int row = e / (D * D), col = e % (D * D);
     const int t1 = row / D, t2 = row % D, s1 = col / D, s2 = col % D;
-    // combined scalar factor pin[s1] pin[s2] pout[t1] pout[t2]
     double fr = ph.re[0][s1], fi = ph.im[0][s1];
     double xr = fr * ph.re[1][s2] - fi * ph.im[1][s2], xi = fr * ph.im[1][s2] + fi * ph.re[1][s2];
     fr = xr * ph.re[2][t1] - xi * ph.im[2][t1]; fi = xr * ph.im[2][t1] + xi * ph.re[2][t1];
@@ -46,22 +48,33 @@ __global__ void __launch_bounds__(128) gate_apply_kernel(cplx* __restrict__ thet
   const long long rowstride = (long long)D * chiR;          // stride of s1 (elements)
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int l = (int)(e / chiR), r = (int)(e % chiR);
+    const int N = qR[r] - qL[l];                           // bosons on the two sites
+    if (N < 0 || N > 2 * (D - 1)) continue;                // no admissible (s1, s2): the entries are exact zeros
+    const int lo = N - (D - 1) > 0 ? N - (D - 1) : 0, hi = N < D - 1 ? N : D - 1;
     cplx* base = theta + (long long)l * D * rowstride + r;
-    cplx in[D * D];
+    cplx in[D];
 #pragma unroll
-    for (int s1 = 0; s1 < D; ++s1)
+    for (int k = 0; k < D; ++k) {
+      const int s1 = lo + k;
+      in[k] = make_double2(0.0, 0.0);
+      if (s1 <= hi) in[k] = base[s1 * rowstride + (long long)(N - s1) * chiR];
+    }
 #pragma unroll
-      for (int s2 = 0; s2 < D; ++s2) in[s1 * D + s2] = base[s1 * rowstride + (long long)s2 * chiR];
-#pragma unroll 1
-    for (int row = 0; row < D * D; ++row) {
+    for (int kt = 0; kt < D; ++kt) {
+      const int t1 = lo + kt;
+      if (t1 > hi) break;
+      const int row = t1 * D + (N - t1);
       double ar = 0.0, ai = 0.0;
 #pragma unroll
-      for (int col = 0; col < D * D; ++col) {
-        const cplx w = W[row * D * D + col];
-        ar += w.x * in[col].x - w.y * in[col].y;
-        ai += w.x * in[col].y + w.y * in[col].x;
+      for (int k = 0; k < D; ++k) {
+        const int s1 = lo + k;
+        if (s1 <= hi) {
+          const cplx w = W[row * D * D + s1 * D + (N - s1)];
+          ar += w.x * in[k].x - w.y * in[k].y;
+          ai += w.x * in[k].y + w.y * in[k].x;
+        }
       }
-      base[(row / D) * rowstride + (long long)(row % D) * chiR] = make_double2(ar, ai);
+      base[t1 * rowstride + (long long)(N - t1) * chiR] = make_double2(ar, ai);
     }
   }
 }
@@ -199,8 +212,8 @@ void launch_merge_setup(GemmDesc* d, const cplx* A1, const cplx* A2, cplx* theta
   merge_setup_kernel<<<1, 32, 0, s>>>(d, A1, A2, theta, dimL, dimM, dimR, D);
 }
 
-void launch_gate_apply(cplx* theta, const int* dimL, const int* dimR, int D, const cplx* G, Phases ph, int maxL, int maxR,
-                       cudaStream_t s) {
+void launch_gate_apply(cplx* theta, const int* dimL, const int* dimR, const int* qL, const int* qR, int D, const cplx* G, Phases ph,
+                       int maxL, int maxR, cudaStream_t s) {
   const int grid = grid_for((long long)maxL * maxR, 128);
   const size_t sm = sizeof(cplx) * D * D * D * D;
   static bool attr8 = false;
@@ -209,13 +222,13 @@ void launch_gate_apply(cplx* theta, const int* dimL, const int* dimR, int D, con
     attr8 = true;
   }
   switch (D) {
-    case 2: gate_apply_kernel<2><<<grid, 128, sm, s>>>(theta, dimL, dimR, G, ph); break;
-    case 3: gate_apply_kernel<3><<<grid, 128, sm, s>>>(theta, dimL, dimR, G, ph); break;
-    case 4: gate_apply_kernel<4><<<grid, 128, sm, s>>>(theta, dimL, dimR, G, ph); break;
-    case 5: gate_apply_kernel<5><<<grid, 128, sm, s>>>(theta, dimL, dimR, G, ph); break;
-    case 6: gate_apply_kernel<6><<<grid, 128, sm, s>>>(theta, dimL, dimR, G, ph); break;
-    case 7: gate_apply_kernel<7><<<grid, 128, sm, s>>>(theta, dimL, dimR, G, ph); break;
-    case 8: gate_apply_kernel<8><<<grid, 128, sm, s>>>(theta, dimL, dimR, G, ph); break;
+    case 2: gate_apply_kernel<2><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, G, ph); break;
+    case 3: gate_apply_kernel<3><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, G, ph); break;
+    case 4: gate_apply_kernel<4><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, G, ph); break;
+    case 5: gate_apply_kernel<5><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, G, ph); break;
+    case 6: gate_apply_kernel<6><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, G, ph); break;
+    case 7: gate_apply_kernel<7><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, G, ph); break;
+    case 8: gate_apply_kernel<8><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, G, ph); break;
     default: break;
   }
 }

@@ -434,7 +434,7 @@ void run_step(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, double from, doubl
           ph.re[2][n] = ph.re[3][n] = u2r[n]; ph.im[2][n] = ph.im[3][n] = u2i[n];
         }
       }
-      launch_gate_apply(ws->theta, m->dim(bl), m->dim(br), D, G, ph, lay.capb[bl], lay.capb[br], s);
+      launch_gate_apply(ws->theta, m->dim(bl), m->dim(br), m->q(bl), m->q(br), D, G, ph, lay.capb[bl], lay.capb[br], s);
       DecompArgs a;
       a.kind = op.c == 0 ? DK_GATE_LEFT : DK_GATE_RIGHT;
       a.D = D;

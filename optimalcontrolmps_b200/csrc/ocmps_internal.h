@@ -111,8 +111,8 @@ void launch_build_factors(const DecompArgs& a, const DecompBuffers& b, int cap_k
 // merge setup: fills desc for theta = A1 (chil*D x chim) * A2 (chim x D*chir)
 void launch_merge_setup(GemmDesc* d, const cplx* A1, const cplx* A2, cplx* theta, const int* dimL, const int* dimM,
                         const int* dimR, int D, cudaStream_t s);
-void launch_gate_apply(cplx* theta, const int* dimL, const int* dimR, int D, const cplx* G, Phases ph, int maxL, int maxR,
-                       cudaStream_t s);
+void launch_gate_apply(cplx* theta, const int* dimL, const int* dimR, const int* qL, const int* qR, int D, const cplx* G, Phases ph,
+                       int maxL, int maxR, cudaStream_t s);
 void launch_site_phase(cplx* A, const int* dimL, const int* dimR, int D, Phases ph, int which, int max_elems, cudaStream_t s);
 void launch_norm_only(const cplx* x, const int* dimL, const int* dimR, int D, double* partial, double* out, int max_elems,
                       cudaStream_t s);

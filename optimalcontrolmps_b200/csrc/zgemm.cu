@@ -36,44 +36,50 @@ __global__ void __launch_bounds__(256) zgemm_kernel(const GemmDesc* __restrict__
 #pragma unroll
   for (int i = 0; i < 8; ++i) { cr[i][0] = cr[i][1] = ci[i][0] = ci[i][1] = 0.0; }
 
+  // global -> registers -> shared staging: the loads of tile k+1 are in flight while tile k is multiplied
+  constexpr int PER = BM * BK / 256;      // elements of each operand per thread and tile (= 4)
+  cplx ra[PER], rb[PER];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int idx = tid + u * 256;
+      {
+        int i, kk;
+        if (d.opA == 0) { i = idx / BK; kk = idx % BK; } else { i = idx % BM; kk = idx / BM; }
+        const int gi = m0 + i, gk = k0 + kk;
+        cplx v = make_double2(0.0, 0.0);
+        if (gi < d.M && gk < d.K) v = d.opA == 0 ? d.A[(size_t)gi * d.lda + gk] : d.A[(size_t)gk * d.lda + gi];
+        if (d.opA) v.y = -v.y;
+        ra[u] = v;
+      }
+      {
+        int kk, j;
+        if (d.opB == 0) { kk = idx / BN; j = idx % BN; } else { kk = idx % BK; j = idx / BK; }
+        const int gk = k0 + kk, gj = n0 + j;
+        cplx v = make_double2(0.0, 0.0);
+        if (gk < d.K && gj < d.N) v = d.opB == 0 ? d.B[(size_t)gk * d.ldb + gj] : d.B[(size_t)gj * d.ldb + gk];
+        if (d.opB) v.y = -v.y;
+        rb[u] = v;
+      }
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int idx = tid + u * 256;
+      int i, kk;
+      if (d.opA == 0) { i = idx / BK; kk = idx % BK; } else { i = idx % BM; kk = idx / BM; }
+      As_re[i][kk] = ra[u].x; As_im[i][kk] = ra[u].y;
+      int kb, j;
+      if (d.opB == 0) { kb = idx / BN; j = idx % BN; } else { kb = idx % BK; j = idx / BK; }
+      Bs_re[kb][j] = rb[u].x; Bs_im[kb][j] = rb[u].y;
+    }
+  };
+  load_tiles(0);
   for (int k0 = 0; k0 < d.K; k0 += BK) {
-    // ---- stage A tile (BM x BK) ----
-    if (d.opA == 0) {
-      for (int idx = tid; idx < BM * BK; idx += 256) {
-        int i = idx / BK, kk = idx % BK;
-        int gi = m0 + i, gk = k0 + kk;
-        cplx v = make_double2(0.0, 0.0);
-        if (gi < d.M && gk < d.K) v = d.A[(size_t)gi * d.lda + gk];
-        As_re[i][kk] = v.x; As_im[i][kk] = v.y;
-      }
-    } else {  // op(A)[i][k] = conj(A[k][i])
-      for (int idx = tid; idx < BM * BK; idx += 256) {
-        int i = idx % BM, kk = idx / BM;
-        int gi = m0 + i, gk = k0 + kk;
-        cplx v = make_double2(0.0, 0.0);
-        if (gi < d.M && gk < d.K) v = d.A[(size_t)gk * d.lda + gi];
-        As_re[i][kk] = v.x; As_im[i][kk] = -v.y;
-      }
-    }
-    // ---- stage B tile (BK x BN) ----
-    if (d.opB == 0) {
-      for (int idx = tid; idx < BK * BN; idx += 256) {
-        int kk = idx / BN, j = idx % BN;
-        int gk = k0 + kk, gj = n0 + j;
-        cplx v = make_double2(0.0, 0.0);
-        if (gk < d.K && gj < d.N) v = d.B[(size_t)gk * d.ldb + gj];
-        Bs_re[kk][j] = v.x; Bs_im[kk][j] = v.y;
-      }
-    } else {  // op(B)[k][j] = conj(B[j][k])
-      for (int idx = tid; idx < BK * BN; idx += 256) {
-        int kk = idx % BK, j = idx / BK;
-        int gk = k0 + kk, gj = n0 + j;
-        cplx v = make_double2(0.0, 0.0);
-        if (gk < d.K && gj < d.N) v = d.B[(size_t)gj * d.ldb + gk];
-        Bs_re[kk][j] = v.x; Bs_im[kk][j] = -v.y;
-      }
-    }
+    store_tiles();
     __syncthreads();
+    if (k0 + BK < d.K) load_tiles(k0 + BK);
 #pragma unroll
     for (int k4 = 0; k4 < BK; k4 += 4) {
       const double ar = As_re[warp * 8 + g][k4 + t];
