@@ -1,0 +1,2 @@
+// shim: see IpTNLP.hpp
+#include "IpTNLP.hpp"

@@ -1,0 +1,97 @@
+// Implementation of the itensor compatibility shim over libocmps.
+#include "itensor/all.h"
+
+#include <cstdlib>
+#include <mutex>
+
+namespace itensor {
+
+ocmps_ctx* default_context() {
+  static ocmps_ctx* ctx = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* e = std::getenv("OCMPS_DEVICE");
+    ocmps_check(ocmps_ctx_create(e ? std::atoi(e) : 0, &ctx), "ocmps_ctx_create");
+  });
+  return ctx;
+}
+
+IQMPS::IQMPS(int L, int D, int chi_cap) : p_(std::make_shared<Holder>()), L_(L), D_(D), cap_(chi_cap) {
+  ocmps_check(ocmps_mps_create(default_context(), L, D, chi_cap, &p_->h), "ocmps_mps_create");
+}
+
+IQMPS::IQMPS(int L, int D, int chi_cap, const std::vector<int>& bond_dims, const std::vector<int>& charges,
+             const std::vector<Cplx>& tensors)
+    : IQMPS(L, D, chi_cap) {
+  ocmps_check(ocmps_mps_upload(p_->h, bond_dims.data(), charges.data(), reinterpret_cast<const double*>(tensors.data()), 0, 2),
+              "ocmps_mps_upload");
+}
+
+IQMPS::IQMPS(const IQMPS& o) : L_(o.L_), D_(o.D_), cap_(o.cap_) {
+  if (o.p_) {
+    p_ = std::make_shared<Holder>();
+    ocmps_check(ocmps_mps_create(default_context(), L_, D_, cap_, &p_->h), "ocmps_mps_create");
+    ocmps_check(ocmps_mps_copy(p_->h, o.p_->h), "ocmps_mps_copy");
+  }
+}
+
+IQMPS& IQMPS::operator=(const IQMPS& o) {
+  if (this != &o) {
+    IQMPS tmp(o);
+    std::swap(p_, tmp.p_);
+    L_ = o.L_; D_ = o.D_; cap_ = o.cap_;
+  }
+  return *this;
+}
+
+std::vector<int> IQMPS::bondDims() const {
+  std::vector<int> d(L_ + 1, 0);
+  if (p_) ocmps_check(ocmps_mps_bond_dims(p_->h, d.data()), "ocmps_mps_bond_dims");
+  return d;
+}
+
+void IQMPS::toHost(std::vector<int>& bond_dims, std::vector<int>& charges, std::vector<Cplx>& tensors) const {
+  long long ne = 0, nq = 0;
+  ocmps_check(ocmps_mps_sizes(p_->h, &ne, &nq), "ocmps_mps_sizes");
+  bond_dims.assign(L_ + 1, 0);
+  charges.assign(nq, 0);
+  tensors.assign(ne, Cplx(0.0, 0.0));
+  int ll = 0, rl = 0;
+  ocmps_check(ocmps_mps_download(p_->h, bond_dims.data(), charges.data(), reinterpret_cast<double*>(tensors.data()), &ll, &rl),
+              "ocmps_mps_download");
+}
+
+IQMPS IQMPS::withCapacity(int chi_cap) const {
+  if (chi_cap == cap_) return *this;
+  std::vector<int> d, q;
+  std::vector<Cplx> t;
+  toHost(d, q, t);
+  return IQMPS(L_, D_, chi_cap, d, q, t);
+}
+
+Real norm(const IQMPS& psi) {
+  double out = 0.0;
+  ocmps_check(ocmps_mps_norm(psi.handle(), &out), "ocmps_mps_norm");
+  return out;
+}
+
+Cplx overlapC(const IQMPS& a, const IQMPS& b) {
+  double o[2];
+  ocmps_check(ocmps_overlap(a.handle(), b.handle(), o), "ocmps_overlap");
+  return Cplx(o[0], o[1]);
+}
+
+Cplx overlapC(const IQMPS& a, const IQMPO& K, const IQMPS& b) {
+  if (K.kind != IQMPO::PropagatorDerivative) throw std::invalid_argument("overlapC: only the propagator derivative MPO is supported");
+  double o[2];
+  ocmps_check(ocmps_overlap_K(a.handle(), b.handle(), o), "ocmps_overlap_K");
+  return Cplx(o[0], o[1]);
+}
+
+void overlap(const IQMPS& a, const IQMPS& b, Real& re, Real& im) {
+  const Cplx z = overlapC(a, b);
+  re = z.real();
+  im = z.imag();
+}
+
+}  // namespace itensor

@@ -1,0 +1,122 @@
+// Drop-in test of the C++ layer: reads a problem + expected results written by tests/test_gpu_cpp_dropin.py
+// (binary, little endian) and drives it exactly like the reference's tests / main programs would:
+// BoseHubbard -> BH_tDMRG -> OptimalControl (GRAPE and GROUP) -> BH_nlp callbacks.  Exit code 0 = all checks pass.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <vector>
+
+#include "BH_nlp.hpp"
+#include "BH_tDMRG.hpp"
+#include "ControlBasisFactory.hpp"
+#include "OptimalControl.hpp"
+
+static std::ifstream in;
+static int failures = 0;
+
+template <typename T> T rd() { T v; in.read(reinterpret_cast<char*>(&v), sizeof(T)); return v; }
+static std::vector<double> rdvec() { int n = rd<int>(); std::vector<double> v(n); in.read(reinterpret_cast<char*>(v.data()), 8 * n); return v; }
+static std::vector<int> rdivec() { int n = rd<int>(); std::vector<int> v(n); in.read(reinterpret_cast<char*>(v.data()), 4 * n); return v; }
+
+static IQMPS rdstate(int L, int D, int cap) {
+  std::vector<int> dims = rdivec(), q = rdivec();
+  std::vector<double> t = rdvec();
+  std::vector<Cplx> tc(t.size() / 2);
+  for (size_t i = 0; i < tc.size(); ++i) tc[i] = Cplx(t[2 * i], t[2 * i + 1]);
+  return IQMPS(L, D, cap, dims, q, tc);
+}
+
+static double relerr(const std::vector<double>& a, const std::vector<double>& b) {
+  double num = 0, den = 1e-300;
+  for (size_t i = 0; i < a.size(); ++i) { num = std::max(num, std::fabs(a[i] - b[i])); den = std::max(den, std::fabs(b[i])); }
+  return num / den;
+}
+static void check(bool ok, const char* what, double val) {
+  printf("%-46s %s (%.3e)\n", what, ok ? "ok" : "FAIL", val);
+  if (!ok) ++failures;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) { fprintf(stderr, "usage: test_dropin problem.bin\n"); return 2; }
+  in.open(argv[1], std::ios::binary);
+  if (!in) { fprintf(stderr, "cannot open %s\n", argv[1]); return 2; }
+  const int L = rd<int>(), d = rd<int>(), N = rd<int>(), M = rd<int>(), maxm = rd<int>(), cap = rd<int>();
+  const double J = rd<double>(), tstep = rd<double>(), T = rd<double>(), cutoff = rd<double>(), gamma = rd<double>(), cs = rd<double>(),
+               ce = rd<double>();
+  auto sites = BoseHubbard(L, d);
+  IQMPS psi_i = rdstate(L, d + 1, cap), psi_f = rdstate(L, d + 1, cap);
+  std::vector<double> u = rdvec(), c = rdvec();
+  const double cost_ref = rd<double>();
+  std::vector<double> fid_ref = rdvec(), grad_ref = rdvec(), hess_ref = rdvec();
+  const double gcost_ref = rd<double>();
+  std::vector<double> ggrad_ref = rdvec(), ghess_ref = rdvec();
+
+  auto stepper = maxm > 0 ? BH_tDMRG(sites, J, tstep, {"Cutoff=", cutoff, "Maxm=", maxm}, cap) : BH_tDMRG(sites, J, tstep, {"Cutoff=", cutoff}, cap);
+  // ---- GRAPE (reference constructor order: target first, init second) ----
+  OptimalControl<BH_tDMRG> OC(psi_f, psi_i, stepper, (size_t)N, gamma);
+  const double cost = OC.getCost(u);
+  check(std::fabs(cost - cost_ref) / std::fabs(cost_ref) < 1e-9, "GRAPE cost", std::fabs(cost - cost_ref) / std::fabs(cost_ref));
+  check(relerr(OC.getFidelityForAllT(u, false), fid_ref) < 1e-9, "GRAPE fidelities (new_control=false)", relerr(OC.getFidelityForAllT(u, false), fid_ref));
+  auto grad = OC.getAnalyticGradient(u, true);
+  check(relerr(grad, grad_ref) < 1e-7, "GRAPE gradient", relerr(grad, grad_ref));
+  auto H = OC.getHessian(u, false);
+  std::vector<double> Hflat;
+  for (auto& r : H) Hflat.insert(Hflat.end(), r.begin(), r.end());
+  check(relerr(Hflat, hess_ref) < 1e-6, "GRAPE Hessian (new_control=false)", relerr(Hflat, hess_ref));
+  OC.setThreadCount(4);
+  auto grad4 = OC.getAnalyticGradient(u, true);
+  check(relerr(grad4, grad) < 1e-11, "gradient, threadCount 4 vs 1", relerr(grad4, grad));
+  bool threw = false;
+  try { OC.setThreadCount(0); } catch (const std::invalid_argument&) { threw = true; }
+  check(threw, "setThreadCount(0) throws std::invalid_argument", 0.0);
+  OC.setBFGS(true);
+  auto gradb = OC.getAnalyticGradient(u, true);
+  check(relerr(gradb, grad) < 1e-11, "gradient, BFGS mode", relerr(gradb, grad));
+  check((int)OC.getPsit().size() == N && linkInd(OC.getPsit().back(), 1).m() >= 1, "getPsit / linkInd", (double)N);
+  // stale-cache contract (tests/SequencingTest.cpp:238-246)
+  std::vector<double> u2(u);
+  for (double& x : u2) x += 1.0;
+  check(std::fabs(OC.getCost(u2, false) - cost) < 1e-10, "stale cost with new_control=false", std::fabs(OC.getCost(u2, false) - cost));
+  // BH_tDMRG::step is a public entry point of its own (main/AnalyzeQuench.cpp:159)
+  IQMPS psi = psi_i;
+  stepper.step(psi, u[0], u[1], true);
+  check(std::fabs(norm(psi) - 1.0) < 1e-12, "BH_tDMRG::step keeps the norm", std::fabs(norm(psi) - 1.0));
+  IQMPS kpsi = exactApplyMPO(stepper.propagatorDeriv(u[0]), psi, stepper.getArgs());
+  const Cplx k1 = overlapC(psi, kpsi), k2 = overlapC(psi, stepper.propagatorDeriv(u[0]), psi);
+  check(std::abs(k1 - k2) < 5e-3 * std::abs(k2), "<psi|K psi> ~ <psi|K|psi> (up to the Maxm truncation)", std::abs(k1 - k2));
+
+  // ---- GROUP ----
+  auto u0 = SeedGenerator::linspace(cs, ce, N);
+  auto basis = ControlBasisFactory::buildChoppedSineBasis(u0, tstep, T, M);
+  OptimalControl<BH_tDMRG> OCG(psi_f, psi_i, stepper, basis, gamma);
+  const double gcost = OCG.getCost(c);
+  check(std::fabs(gcost - gcost_ref) / std::fabs(gcost_ref) < 1e-9, "GROUP cost", std::fabs(gcost - gcost_ref) / std::fabs(gcost_ref));
+  check(relerr(OCG.getAnalyticGradient(c, true), ggrad_ref) < 1e-7, "GROUP gradient", relerr(OCG.getAnalyticGradient(c, false), ggrad_ref));
+  auto GH = OCG.getHessian(c, false);
+  std::vector<double> GHflat;
+  for (auto& r : GH) GHflat.insert(GHflat.end(), r.begin(), r.end());
+  check(relerr(GHflat, ghess_ref) < 1e-6, "GROUP Hessian", relerr(GHflat, ghess_ref));
+
+  // ---- BH_nlp callbacks as IPOPT would issue them ----
+  BH_nlp nlp(OCG, false);
+  Ipopt::Index n, m, nj, nh;
+  TNLP::IndexStyleEnum style;
+  nlp.get_nlp_info(n, m, nj, nh, style);
+  check(n == M && m == N && nj == N * M && nh == (M * M + M) / 2 && style == TNLP::C_STYLE, "BH_nlp::get_nlp_info", (double)n);
+  std::vector<double> xl(n), xu(n), gl(m), gu(m), x(c), g(m), gf(n), hv(nh);
+  nlp.get_bounds_info(n, xl.data(), xu.data(), m, gl.data(), gu.data());
+  check(xl[0] == -20 && xu[0] == 20 && gl[0] == 2.0 && gu[0] == 100, "BH_nlp::get_bounds_info", xl[0]);
+  double f = 0;
+  nlp.eval_g(n, x.data(), true, m, g.data());
+  nlp.eval_f(n, x.data(), false, f);
+  nlp.eval_grad_f(n, x.data(), false, gf.data());
+  check(std::fabs(f - gcost_ref) / std::fabs(gcost_ref) < 1e-9, "BH_nlp::eval_f after eval_g(new_x)", std::fabs(f - gcost_ref));
+  check(relerr(gf, ggrad_ref) < 1e-7, "BH_nlp::eval_grad_f (new_x=false)", relerr(gf, ggrad_ref));
+  nlp.eval_h(n, x.data(), false, 2.0, m, nullptr, false, nh, nullptr, nullptr, hv.data());
+  check(std::fabs(hv[0] - 2.0 * ghess_ref[0]) < 1e-6 * std::fabs(2.0 * ghess_ref[0]) + 1e-12, "BH_nlp::eval_h (obj_factor 2)", hv[0]);
+
+  printf("%s: %d failure(s)\n", failures ? "FAILED" : "PASSED", failures);
+  return failures ? 1 : 0;
+}
