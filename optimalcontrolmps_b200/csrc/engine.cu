@@ -10,14 +10,18 @@
 #include <complex>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 #include <string>
+#include <atomic>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "ocmps_internal.h"
 #include "../../include/ocmps.h"
 
-long long g_ocmps_launches = 0;
+std::atomic<long long> g_ocmps_launches{0};
 
 namespace {
 
@@ -168,6 +172,9 @@ int alloc_mps(ocmps_ctx* ctx, int L, int D, int cap, ocmps_mps** out, int mult =
   CK(cudaMemset(m->d_dims, 0, sizeof(int) * (L + 1)));
   CK(cudaMemset(m->d_q, 0, sizeof(int) * (size_t)(L + 1) * cap));
   for (int j = 0; j < L; ++j) m->cur[j] = 0;
+  // the memsets above run on the legacy default stream, which does not order against the engine's non-blocking
+  // streams: make sure they have landed before any chain touches the new buffers
+  CK(cudaDeviceSynchronize());
   *out = m;
   return OCMPS_OK;
 }
@@ -966,6 +973,7 @@ int ocmps_store_create(ocmps_ctx* ctx, int L, int D, int chi_cap, int nslots, oc
   CK(cudaMalloc(&s->dims, sizeof(int) * (size_t)(L + 1) * nslots));
   CK(cudaMalloc(&s->q, sizeof(int) * (size_t)(L + 1) * chi_cap * nslots));
   CK(cudaMemset(s->dims, 0, sizeof(int) * (size_t)(L + 1) * nslots));
+  CK(cudaDeviceSynchronize());
   *out = s;
   return OCMPS_OK;
 }
@@ -1214,47 +1222,76 @@ int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* x
   CK(cudaMemset(d_ovl, 0, sizeof(cplx) * (size_t)Nt * Nt));
   CK(cudaMemset(d_norms, 0, sizeof(double) * Nt));
   CK(cudaDeviceSynchronize());
-  // longest rows first, dealt round-robin to the chains; chains advance in lock step so every stream stays fed
+  // longest rows first, dealt round-robin to the chains.  Host threads (the reference's work-queue threads,
+  // src/OptimalControl.cpp:305-335) each drive a subset of the chains; a thread advances its chains in lock step so
+  // that all of its streams stay fed.
   std::vector<int> order(rows, rows + nrows);
   std::sort(order.begin(), order.end());
   struct ChainState { int row = -1; int j = 0; size_t next = 0; };
   std::vector<std::vector<int>> mine(nchains);
   for (int i = 0; i < nrows; ++i) mine[i % nchains].push_back(order[i]);
   std::vector<ChainState> cs(nchains);
-  bool busy = true;
-  rc = OCMPS_OK;
-  while (busy && !rc) {
-    busy = false;
-    for (int c = 0; c < nchains && !rc; ++c) {
-      ChainState& S = cs[c];
-      Workspace* ws = wss[c];
-      if (S.row < 0) {
-        if (S.next >= mine[c].size()) continue;
-        S.row = mine[c][S.next++];
-        if (S.row < 1 || S.row > Nt - 2) { rc = fail(OCMPS_ERR_INVALID, "hessian row out of range [1, Nt-2]"); break; }
-        // psiH = K|psi_row>, its norm, diagonal overlap (src/OptimalControl.cpp:256-264)
-        rc = store_get_async(psi_store, S.row, ws->work, ws->stream);
-        if (!rc) rc = apply_K_async(st, ws, ws->work, psiH[c], ws->stream);
-        if (rc) break;
-        launch_norm_only(psiH[c]->site(0), psiH[c]->dim(0), psiH[c]->dim(1), st->D, ws->db.partial, d_norms + S.row, 0, ws->stream);
-        g_ocmps_launches += 2;
-        rc = overlaps_async(ws, side_of_store(xiH_store, S.row), xiH_store->lay, side_of_mps(psiH[c]), psiH[c]->lay, 1, 0, ws->stream);
-        if (rc) break;
-        CK(cudaMemcpyAsync(d_ovl + (size_t)S.row * Nt + S.row, ws->d_out, sizeof(cplx), cudaMemcpyDeviceToDevice, ws->stream));
-        S.j = S.row + 1;
-        busy = true;
-      } else {
-        if (S.j >= Nt - 1) { S.row = -1; busy = true; continue; }
-        // one step forward and the overlap with xiH_j (:267-277)
-        run_step(st, psiH[c], ws, u[S.j - 1], u[S.j], true, ws->stream);
-        rc = overlaps_async(ws, side_of_store(xiH_store, S.j), xiH_store->lay, side_of_mps(psiH[c]), psiH[c]->lay, 1, 0, ws->stream);
-        if (rc) break;
-        CK(cudaMemcpyAsync(d_ovl + (size_t)S.row * Nt + S.j, ws->d_out, sizeof(cplx), cudaMemcpyDeviceToDevice, ws->stream));
-        ++S.j;
-        busy = true;
+  const int hw = (int)std::thread::hardware_concurrency();
+  (void)hw;
+  int nthreads = 1;      // measured: the rows are GPU bound, extra launch threads do not help (OCMPS_HESSIAN_THREADS overrides)
+  if (const char* e = getenv("OCMPS_HESSIAN_THREADS")) nthreads = std::max(1, std::min(nchains, atoi(e)));
+  std::mutex err_mutex;
+  std::string err_msg;
+  int err_rc = OCMPS_OK;
+  auto worker = [&](int t) {
+    cudaSetDevice(st->ctx->dev);
+    int lrc = OCMPS_OK;
+    bool busy = true;
+    while (busy && !lrc) {
+      busy = false;
+      for (int c = t; c < nchains && !lrc; c += nthreads) {
+        ChainState& S = cs[c];
+        Workspace* ws = wss[c];
+        if (S.row < 0) {
+          if (S.next >= mine[c].size()) continue;
+          S.row = mine[c][S.next++];
+          if (S.row < 1 || S.row > Nt - 2) { lrc = fail(OCMPS_ERR_INVALID, "hessian row out of range [1, Nt-2]"); break; }
+          // psiH = K|psi_row>, its norm, diagonal overlap (src/OptimalControl.cpp:256-264)
+          lrc = store_get_async(psi_store, S.row, ws->work, ws->stream);
+          if (!lrc) lrc = apply_K_async(st, ws, ws->work, psiH[c], ws->stream);
+          if (lrc) break;
+          launch_norm_only(psiH[c]->site(0), psiH[c]->dim(0), psiH[c]->dim(1), st->D, ws->db.partial, d_norms + S.row, 0, ws->stream);
+          g_ocmps_launches += 2;
+          lrc = overlaps_async(ws, side_of_store(xiH_store, S.row), xiH_store->lay, side_of_mps(psiH[c]), psiH[c]->lay, 1, 0, ws->stream);
+          if (lrc) break;
+          if (cudaMemcpyAsync(d_ovl + (size_t)S.row * Nt + S.row, ws->d_out, sizeof(cplx), cudaMemcpyDeviceToDevice, ws->stream) != cudaSuccess) {
+            lrc = fail(OCMPS_ERR_CUDA, "cudaMemcpyAsync failed"); break;
+          }
+          S.j = S.row + 1;
+          busy = true;
+        } else {
+          if (S.j >= Nt - 1) { S.row = -1; busy = true; continue; }
+          // one step forward and the overlap with xiH_j (:267-277)
+          run_step(st, psiH[c], ws, u[S.j - 1], u[S.j], true, ws->stream);
+          lrc = overlaps_async(ws, side_of_store(xiH_store, S.j), xiH_store->lay, side_of_mps(psiH[c]), psiH[c]->lay, 1, 0, ws->stream);
+          if (lrc) break;
+          if (cudaMemcpyAsync(d_ovl + (size_t)S.row * Nt + S.j, ws->d_out, sizeof(cplx), cudaMemcpyDeviceToDevice, ws->stream) != cudaSuccess) {
+            lrc = fail(OCMPS_ERR_CUDA, "cudaMemcpyAsync failed"); break;
+          }
+          ++S.j;
+          busy = true;
+        }
       }
     }
+    if (lrc) {
+      std::lock_guard<std::mutex> lock(err_mutex);
+      if (!err_rc) { err_rc = lrc; err_msg = g_err; }
+    }
+  };
+  if (nthreads == 1) {
+    worker(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t) pool.emplace_back(worker, t);
+    for (auto& th : pool) th.join();
   }
+  rc = err_rc;
+  if (rc) g_err = err_msg;
   cudaDeviceSynchronize();
   if (!rc) {
     cudaMemcpy(ovl, d_ovl, sizeof(cplx) * (size_t)Nt * Nt, cudaMemcpyDeviceToHost);

@@ -60,7 +60,8 @@ struct SiteOffs { long long o[OCMPS_MAX_L + 1]; };
 // diagonal on-site phases around the J gate: [0] in on site 1, [1] in on site 2, [2] out on site 1, [3] out on site 2
 struct Phases { double re[4][OCMPS_MAX_D]; double im[4][OCMPS_MAX_D]; };
 
-extern long long g_ocmps_launches;   // kernels launched so far (bench.py reports it)
+#include <atomic>
+extern std::atomic<long long> g_ocmps_launches;   // kernels launched so far (bench.py reports it)
 
 void debug_jacobi_counters(unsigned long long* out, bool reset);
 void profile_enable(bool on);
