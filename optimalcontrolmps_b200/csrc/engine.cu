@@ -387,8 +387,8 @@ void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int c
   int nblk = std::min(OCMPS_MAX_BLK, std::max(capV, capC) + a.D);
   const bool need_global = need > JAC_SMEM_LIMIT;    // some block may not fit in shared memory
   // numerical-rank tolerance of the pivoted QR: the neglected weight stays >= 6 orders below the cutoff
-  double rank_tol = 1e-8 * tp.cutoff;
-  rank_tol = std::min(1e-16, std::max(1e-30, rank_tol));
+  double rank_tol = 1e-6 * tp.cutoff;
+  rank_tol = std::min(1e-14, std::max(1e-30, rank_tol));
   launch_jacobi_blocks(a, ws->db, nblk, smem, need_global, rank_tol, s);
   launch_truncate(a, ws->db, tp, s);
   launch_build_factors(a, ws->db, capK, capV, capC, s);
