@@ -469,17 +469,22 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) truncate_kernel(DecompArgs a, DecompBuffers b, TruncParams tp) {
   __shared__ double sP[NV_MAX];
-  __shared__ double sSorted[NV_MAX];
+  __shared__ double sSorted[NV_MAX];      // descending; later overwritten by its suffix sums
   __shared__ short sQ[NV_MAX];
   __shared__ unsigned char sKeep[NV_MAX];
   __shared__ short sPos[NV_MAX];
+  __shared__ int sBlkOff[OCMPS_MAX_BLK + 1];
+  __shared__ double sWarp[32];
   __shared__ double s_docut;
-  __shared__ int s_total;
+  __shared__ int s_total, s_nfinal;
+  __shared__ double s_kept;
   DecompWork* w = b.dw;
   const int nv = w->nvtot;
-  const int tid = threadIdx.x;
+  const int nblocks = w->nblocks;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < nv; i += blockDim.x) { sP[i] = b.P[i]; sQ[i] = (short)b.vecq[i]; }
-  if (tid == 0) s_total = 0;
+  for (int i = tid; i < nblocks; i += blockDim.x) sBlkOff[i] = w->blk[i].p_off;
+  if (tid == 0) { s_total = 0; s_nfinal = 0; }
   __syncthreads();
   for (int i = tid; i < nv; i += blockDim.x) {
     const double pi = sP[i];
@@ -491,32 +496,70 @@ __global__ void __launch_bounds__(1024) truncate_kernel(DecompArgs a, DecompBuff
     sSorted[rank] = pi;
   }
   __syncthreads();
-  if (tid == 0) {
-    double docut = 0.0;
-    const int origm = nv;
-    if (origm == 1) {
-      docut = sSorted[0] / 2.0;
-    } else if (origm > 1) {
-      int n = origm - 1;
-      double truncerr = 0.0;
-      while (n >= tp.maxm) { truncerr += sSorted[n]; --n; }
-      double scale = 1.0;
-      if (tp.rel_cutoff) {
-        double sum = 0.0;
-        for (int i = 0; i < origm; ++i) sum += sSorted[i];
-        scale = (sum == 0.0) ? 1.0 : sum;
-      }
-      while (n >= tp.minm && truncerr + sSorted[n] < tp.cutoff * scale) { truncerr += sSorted[n]; --n; }
-      if (n < 0) n = 0;
-      const int m = n + 1;
-      if (m < origm) {
-        docut = (sSorted[m] + sSorted[m - 1]) / 2.0;
-        if (fabs(sSorted[m] - sSorted[m - 1]) < 1e-3 * sSorted[m - 1]) docut += 1e-3 * sSorted[m - 1];
-      }
+  // Suffix sums Suf[n] = sum_{i >= n} sorted[i] (what ITensor's loop accumulates in `truncerr` while it walks down
+  // from the small end), by a block-wide scan: thread t owns the two entries 2t, 2t+1 counted from the END.
+  const int origm = nv;
+  const int e0 = origm - 1 - 2 * tid, e1 = e0 - 1;         // e0 > e1
+  const double v0 = e0 >= 0 ? sSorted[e0] : 0.0, v1 = e1 >= 0 ? sSorted[e1] : 0.0;
+  {
+    double run = v0 + v1;                                   // inclusive scan over threads (towards smaller indices)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double up = __shfl_up_sync(0xffffffffu, run, o);
+      if (lane >= o) run += up;
     }
-    s_docut = docut;
+    if (lane == 31) sWarp[warp] = run;
+    __syncthreads();
+    if (warp == 0) {
+      double ws = sWarp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, ws, o);
+        if (lane >= o) ws += up;
+      }
+      sWarp[lane] = ws;
+    }
+    __syncthreads();
+    const double base = warp > 0 ? sWarp[warp - 1] : 0.0;
+    const double incl = base + run;                         // sum over entries >= e1
+    if (e0 >= 0) sSorted[e0] = incl - v1;                   // Suf[e0]
+    if (e1 >= 0) sSorted[e1] = incl;                        // Suf[e1]
   }
   __syncthreads();
+  {
+    // final n = largest n <= min(maxm, origm) - 1 with (n < minm or Suf[n] >= cutoff * scale)
+    const double scale = tp.rel_cutoff ? (sSorted[0] == 0.0 ? 1.0 : sSorted[0]) : 1.0;
+    const double cut = tp.cutoff * scale;
+    const int nmax = (tp.maxm < origm ? tp.maxm : origm) - 1;
+    int best = 0;
+    for (int n = tid; n <= nmax; n += blockDim.x)
+      if (n < tp.minm || sSorted[n] >= cut) best = n > best ? n : best;
+    if (best > 0) atomicMax(&s_nfinal, best);
+  }
+  __syncthreads();
+  {
+    // docut = midpoint of the two sorted values that straddle the cut (+ the degeneracy bump)
+    const int m = s_nfinal + 1;
+    if (origm == 1) {
+      if (e0 == 0) s_docut = v0 / 2.0;
+    } else if (m < origm) {
+      if (e0 == m) sWarp[0] = v0;
+      if (e1 == m) sWarp[0] = v1;
+      if (e0 == m - 1) sWarp[1] = v0;
+      if (e1 == m - 1) sWarp[1] = v1;
+    } else if (tid == 0) {
+      s_docut = 0.0;
+    }
+    __syncthreads();
+    if (tid == 0 && origm > 1 && m < origm) {
+      const double pm = sWarp[0], pm1 = sWarp[1];
+      double docut = (pm + pm1) / 2.0;
+      if (fabs(pm - pm1) < 1e-3 * pm1) docut += 1e-3 * pm1;
+      s_docut = docut;
+    }
+    if (tid == 0 && origm == 0) s_docut = 0.0;
+    __syncthreads();
+  }
   const double docut = s_docut;
   for (int i = tid; i < nv; i += blockDim.x) {
     const unsigned char k = sP[i] > docut;
@@ -546,23 +589,37 @@ __global__ void __launch_bounds__(1024) truncate_kernel(DecompArgs a, DecompBuff
       if (pos < tp.cap) {
         a.qNew[pos] = qi;
         int bi = 0;                      // block of vector i: scan the (short) block table
-        while (bi + 1 < w->nblocks && w->blk[bi + 1].p_off <= i) ++bi;
+        while (bi + 1 < nblocks && sBlkOff[bi + 1] <= i) ++bi;
         inv_blk[pos] = bi;
-        inv_v[pos] = i - w->blk[bi].p_off;
+        inv_v[pos] = i - sBlkOff[bi];
       }
     }
     b.pos[i] = pos;
     sPos[i] = (short)pos;
   }
   __syncthreads();
+  {
+    // sum of the kept weights: per-thread partial sums over a fixed index pattern, fixed-order tree
+    double part = 0.0;
+    for (int i = tid; i < nv; i += blockDim.x) if (sKeep[i] && sPos[i] < tp.cap) part += sP[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) sWarp[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int i = 0; i < 32; ++i) t += sWarp[i];
+      s_kept = t;
+    }
+    __syncthreads();
+  }
   if (tid == 0) {
     int k = total;
     if (k > tp.cap) { atomicOr(b.status, OCMPS_ST_CAPACITY); k = tp.cap; }
     w->newdim = k;
     *a.dimNew = k;
     // Frobenius norm of the tensor that carries the centre = sqrt(sum of kept weights), fixed summation order
-    double kept = 0.0;
-    for (int i = 0; i < nv; ++i) if (sKeep[i] && sPos[i] < tp.cap) kept += sP[i];
+    const double kept = s_kept;
     double scale = 1.0;
     if (tp.normalize) {
       const double nrm = sqrt(kept);
