@@ -185,9 +185,9 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_rot, s_keff, s_big;
   __shared__ double s_F;
-  __shared__ double s_nrm[JAC_NV_SMEM];
+  __shared__ double s_nrm[JAC_NV_SMEM], s_nrm2[JAC_NV_SMEM], s_nrmref[JAC_NV_SMEM];
   __shared__ double s_rdr[JAC_NV_SMEM], s_rdi[JAC_NV_SMEM];   // diagonal of R
-  __shared__ short s_perm[JAC_NV_SMEM];
+  __shared__ short s_perm[JAC_NV_SMEM], s_permA[JAC_NV_SMEM], s_permB[JAC_NV_SMEM];
   const DecompWork* w = b.dw;
   if ((int)blockIdx.x >= w->nblocks) return;
   const DecompBlock B = w->blk[blockIdx.x];
@@ -203,7 +203,11 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   double* rdr = SMEM ? s_rdr : (b.scratch_d + 2 * B.p_off);
   double* rdi = rdr + (SMEM ? JAC_NV_SMEM : nv);
   if (SMEM) rdi = s_rdi;
-  short* perm = SMEM ? s_perm : reinterpret_cast<short*>(b.scratch_d + 2 * NV_MAX) + B.p_off;
+  short* perm = SMEM ? s_perm : reinterpret_cast<short*>(b.scratch_d + 4 * NV_MAX) + B.p_off;            // final order
+  short* permA = SMEM ? s_permA : reinterpret_cast<short*>(b.scratch_d + 5 * NV_MAX) + B.p_off;          // ping-pong
+  short* permB = SMEM ? s_permB : reinterpret_cast<short*>(b.scratch_d + 6 * NV_MAX) + B.p_off;
+  double* nrm2 = SMEM ? s_nrm2 : (b.scratch_d + 2 * NV_MAX + B.p_off);
+  double* nrmref = SMEM ? s_nrmref : (b.scratch_d + 3 * NV_MAX + B.p_off);
   const int* vidx = b.vec_idx + B.vec_off;
   const int* cidx = b.comp_idx + B.comp_off;
 
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
     double s = 0.0;
     for (int c = lane; c < len; c += 32) { cplx u = y[c]; s += u.x * u.x + u.y * u.y; }
     s = warp_sum(s);
-    if (lane == 0) { nrm[v] = s; perm[v] = (short)v; }
+    if (lane == 0) { nrm[v] = s; nrmref[v] = s; perm[v] = (short)v; permA[v] = (short)v; }
   }
   __syncthreads();
   if (tid == 0) {
@@ -241,13 +245,19 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
 
   const long long t_qr0 = clock64();
   // ---- phase 1: Householder QR with column pivoting, in place; R's strict upper part and rdiag remain ----
+  // One barrier per step: the trailing norms and the position->slot map are double buffered, so the updates of
+  // step j (written to the "next" copies) cannot disturb a warp that is still selecting the pivot of step j.
+  // Trailing norms are downdated (|y|^2 -= |r_ji|^2) and recomputed exactly only when cancellation has eaten
+  // half of the digits since the last exact value (the LAPACK xGEQP3 safeguard).
   const int kmax = nv < len ? nv : len;
   int keff = 0;
+  double* ncur = nrm;  double* nnext = nrm2;
+  short* pcur = permA; short* pnext = permB;
   for (int j = 0; j < kmax; ++j) {
     // pivot: every warp finds the same argmax of the trailing norms (ties -> smaller position)
     double best = -1.0; int bpos = j;
     for (int i = j + lane; i < nv; i += 32) {
-      const double t = nrm[perm[i]];
+      const double t = ncur[pcur[i]];
       if (t > best) { best = t; bpos = i; }
     }
 #pragma unroll
@@ -258,24 +268,24 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
     }
     if (!(best > rtol_abs)) break;         // numerical rank reached: the trailing block is negligible
     keff = j + 1;
-    const int pv = perm[bpos];             // physical slot of the pivot vector
-    const int pj = perm[j];
-    __syncthreads();                        // everybody has read perm before it is swapped
-    if (tid == 0) { perm[j] = (short)pv; perm[bpos] = (short)pj; }
+    const int pv = pcur[bpos];             // physical slot of the pivot vector
+    const int pj = pcur[j];
     const cplx* x = Y + pv * len;          // Householder vector: x[j..len), with x[j] replaced by v0
     const cplx alpha = x[j];
-    const double normx = sqrt(best);
-    const double aabs = sqrt(alpha.x * alpha.x + alpha.y * alpha.y);
-    const double phr = aabs > 0.0 ? alpha.x / aabs : 1.0, phi = aabs > 0.0 ? alpha.y / aabs : 0.0;
+    const double inx = rsqrt(best), normx = best * inx;
+    const double a2 = alpha.x * alpha.x + alpha.y * alpha.y;
+    const double ia = a2 > 0.0 ? rsqrt(a2) : 0.0, aabs = a2 * ia;
+    const double phr = a2 > 0.0 ? alpha.x * ia : 1.0, phi = a2 > 0.0 ? alpha.y * ia : 0.0;
     const double v0r = alpha.x + phr * normx, v0i = alpha.y + phi * normx;
-    const double beta = 1.0 / (normx * (normx + aabs));
-    if (tid == 0) { rdr[j] = -phr * normx; rdi[j] = -phi * normx; nrm[pv] = -2.0; }   // R_jj; pivot leaves the candidate set
-    __syncthreads();                        // perm swapped
+    const double rb = rsqrt(normx * (normx + aabs));
+    const double beta = rb * rb;
+    if (tid == 0) { rdr[j] = -phr * normx; rdi[j] = -phi * normx; perm[j] = (short)pv; }   // R_jj; final position j
     // apply H = I - beta v v^H to the remaining vectors, one half-warp per vector
     for (int ib = j + 1 + 2 * warp; ib < nv; ib += 2 * nwarps) {
       const int i = ib + half;
       const bool act = i < nv;
-      cplx* y = Y + (act ? (int)perm[i] : pv) * len;
+      const int phys = act ? (i == bpos ? pj : (int)pcur[i]) : pv;
+      cplx* y = Y + phys * len;
       double wr = 0.0, wi = 0.0;
       if (act) {
         for (int c = j + hl; c < len; c += 16) {
@@ -287,7 +297,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
         }
       }
       wr = half_sum(wr); wi = half_sum(wi);
-      double tail = 0.0;
+      double rji2 = 0.0;
       if (act) {
         const double fr = beta * wr, fi = beta * wi;
         for (int c = j + hl; c < len; c += 16) {
@@ -297,14 +307,30 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
           yy.x -= fr * vv.x - fi * vv.y;
           yy.y -= fr * vv.y + fi * vv.x;
           y[c] = yy;
-          if (c > j) tail += yy.x * yy.x + yy.y * yy.y;
+          if (c == j) rji2 = yy.x * yy.x + yy.y * yy.y;
         }
       }
-      tail = half_sum(tail);
-      if (act && hl == 0) nrm[perm[i]] = tail;
+      // the lane that owns component j holds |r_ji|^2: broadcast inside the half-warp
+      rji2 = __shfl_sync(0xffffffffu, rji2, lane & 16);        // component j is owned by lane 0 of the half-warp
+      double tnew = 0.0;
+      bool redo = false;
+      if (act) {
+        tnew = ncur[phys] - rji2;
+        redo = !(tnew > 1.5e-8 * nrmref[phys]);
+      }
+      if (__any_sync(0xffffffffu, redo)) {     // rare: exact trailing norm
+        double tail = 0.0;
+        if (act && redo) for (int c = j + 1 + hl; c < len; c += 16) { const cplx yy = y[c]; tail += yy.x * yy.x + yy.y * yy.y; }
+        tail = half_sum(tail);
+        if (act && redo) { tnew = tail; if (hl == 0) nrmref[phys] = tail; }
+      }
+      if (act && hl == 0) { nnext[phys] = tnew > 0.0 ? tnew : 0.0; pnext[i] = (short)phys; }
     }
     __syncthreads();
+    { double* t = ncur; ncur = nnext; nnext = t; short* u = pcur; pcur = pnext; pnext = u; }
   }
+  for (int i = keff + tid; i < nv; i += JAC_THREADS) perm[i] = pcur[i];     // positions past the numerical rank
+  __syncthreads();
   if (tid == 0) s_keff = keff;
 
   // ---- phase 2: R (keff x nv, position order) -> row-major scratch -> back as the Jacobi working set ----

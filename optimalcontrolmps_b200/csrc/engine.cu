@@ -201,7 +201,7 @@ int alloc_ws(ocmps_ctx* ctx, int L, int D, int cap, bool with_work, Workspace** 
   CK(cudaMalloc(&w->db.pos, sizeof(int) * 3 * NV_MAX));
   CK(cudaMalloc(&w->db.ywork, sizeof(cplx) * 2 * nD * cap));
   w->db.ywork_half = (long long)(nD * cap);
-  CK(cudaMalloc(&w->db.scratch_d, sizeof(double) * 3 * NV_MAX));
+  CK(cudaMalloc(&w->db.scratch_d, sizeof(double) * 8 * NV_MAX));
   CK(cudaMalloc(&w->db.descs, sizeof(GemmDesc) * 4));
   CK(cudaMalloc(&w->db.partial, sizeof(double) * 64));
   CK(cudaMalloc(&w->d_norm, sizeof(double) * 4));

@@ -97,7 +97,7 @@ struct DecompBuffers {
   int* pos;                       // new bond index of each vector (-1: dropped)
   cplx* ywork;                    // region A: right vectors Z block after block; region B (+ywork_half): scratch
   long long ywork_half;
-  double* scratch_d;              // 3*NV_MAX doubles (global-memory fallback of the block kernel)
+  double* scratch_d;              // 8*NV_MAX doubles (global-memory fallback of the block kernel)
   GemmDesc* descs;                // [1] neighbour gemm of gauge moves, [2] two-site merge
   double* partial;                // norm partial sums
   int* status;
