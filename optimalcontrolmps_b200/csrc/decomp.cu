@@ -369,8 +369,10 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
     for (int r = 0; r < npad - 1; ++r) {
       for (int kb = 2 * warp; kb < npairs; kb += 2 * nwarps) {     // warp-uniform trip count
         const int k = kb + half;
-        int p = (r + k) % (npad - 1);
-        int q = (k == 0) ? (npad - 1) : (r + npad - 1 - k) % (npad - 1);
+        // round-robin pairing without integer division: p = (r + k) mod (npad-1), q = (r - k) mod (npad-1); r, k < npad-1
+        int p = r + k; if (p >= npad - 1) p -= npad - 1;
+        int q = r - k; if (q < 0) q += npad - 1;
+        if (k == 0) q = npad - 1;
         const bool act = (k < npairs) && p < keff && q < keff;
         if (p > q) { int tmp = p; p = q; q = tmp; }
         cplx* yp = Z + (act ? p : 0) * nv;
@@ -382,12 +384,21 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
 #pragma unroll
             for (int e = 0; e < JAC_EPL; ++e) {
               const int c = hl + 16 * e;
-              if (c < nv) {
-                ru[e] = yp[c]; rv[e] = yq[c];
-                cre += ru[e].x * rv[e].x + ru[e].y * rv[e].y;      // conj(u) * v
-                cim += ru[e].x * rv[e].y - ru[e].y * rv[e].x;
-              }
+              ru[e] = make_double2(0.0, 0.0); rv[e] = make_double2(0.0, 0.0);
+              if (c < nv) { ru[e] = yp[c]; rv[e] = yq[c]; }
             }
+            // conj(u) * v with short dependency chains: independent products, pairwise tree
+            double pr[JAC_EPL], pi[JAC_EPL];
+#pragma unroll
+            for (int e = 0; e < JAC_EPL; ++e) {
+              pr[e] = ru[e].x * rv[e].x + ru[e].y * rv[e].y;
+              pi[e] = ru[e].x * rv[e].y - ru[e].y * rv[e].x;
+            }
+#pragma unroll
+            for (int w2 = JAC_EPL / 2; w2 > 0; w2 >>= 1)
+#pragma unroll
+              for (int e = 0; e < w2; ++e) { pr[e] += pr[e + w2]; pi[e] += pi[e + w2]; }
+            cre = pr[0]; cim = pi[0];
           } else {
             for (int c = hl; c < nv; c += 16) {
               cplx u = yp[c], v = yq[c];
