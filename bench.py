@@ -320,6 +320,8 @@ def run_ours(args):
                                     "sample": f"oracle port (NumPy/OpenBLAS, {ncores} threads): 1 forward + 1 backward Trotter step and 1 MPO "
                                               f"overlap from each of 8 evenly spaced slices of this run's psi_t / xi_t, extrapolated to "
                                               f"2*(Nt-1) steps + Nt+1 overlaps", **det}
+        if args.batch > 1 and world == 1:
+            line["batched"] = batched_bench(args.batch, oc, st, psi_i, psi_f, ocp, c)
         if args.hessian_nt:
             line["hessian"] = hessian_bench(args.hessian_nt, oc, ocd, st, psi_i, psi_f, world, dev, torch)
         print(json.dumps(line), flush=True)
@@ -328,6 +330,25 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def batched_bench(B, oc, st, psi_i, psi_f, ocp0, c0):
+    """B independent controls evaluated concurrently on ONE GPU (2B sweeps on 2B streams): the batched-seeds workload of
+    the north star.  Reported next to the single-evaluation headline, never instead of it."""
+    probs, ctrls = [], []
+    for k in range(B):
+        basis, c, _ = make_problem_host(100 + k)
+        probs.append(oc.OptimalControl(psi_f, psi_i, st, basis, CFG["gamma"]))
+        ctrls.append(list(c))
+    oc.batch_cost_gradient(probs, ctrls)                    # warm-up (allocates the per-chain workspaces)
+    t0 = time.perf_counter()
+    res = oc.batch_cost_gradient(probs, ctrls)
+    dt = time.perf_counter() - t0
+    # consistency with the single-evaluation path on the first control
+    g1 = probs[0].getAnalyticGradient(ctrls[0], True)
+    c1 = probs[0].getCost(ctrls[0], False)
+    return {"evals_in_flight": B, "value": B / dt, "unit": UNIT, "seconds": dt,
+            "max_abs_diff_vs_single": float(max(abs(res[0][0] - c1), np.max(np.abs(np.array(res[0][1]) - np.array(g1)))))}
 
 
 def hessian_bench(Nt, oc, ocd, st, psi_i, psi_f, world, dev, torch):
@@ -359,6 +380,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--hessian-nt", type=int, default=0, help="additionally time a sharded GRAPE Hessian with this many time points")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=6, help="additionally time this many independent controls in flight on one GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

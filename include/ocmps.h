@@ -99,6 +99,11 @@ int ocmps_backward_sweep(ocmps_stepper* st, ocmps_mps* psi_target, const double*
 /* both sweeps enqueued on two streams (the reference's two std::threads, :424-430) */
 int ocmps_sweep_pair(ocmps_stepper* st, ocmps_mps* psi_init, ocmps_mps* psi_target, const double* u, int Nt,
                      ocmps_store* psi_store, ocmps_store* xi_store);
+/* batches of independent controls (north_star; SeedGenerator fan-out of main/OptimizeRamp.cpp:60,83): `nchains` sweeps, chain c
+ * starts from starts[c], runs forward (forward[c]=1, like calcPsi) or backward (like calcXi) under the controls
+ * u[c*Nt .. c*Nt+Nt) and fills stores[c]; every chain has its own stream, one synchronisation at the end */
+int ocmps_sweep_batch(ocmps_stepper* st, int nchains, ocmps_mps** starts, const int* forward, const double* u, int Nt,
+                      ocmps_store** stores);
 /* BFGS branch (:217-229): xi is propagated backwards without being stored, divT filled on the fly */
 int ocmps_backward_sweep_divT(ocmps_stepper* st, ocmps_mps* psi_target, const double* u, int Nt, ocmps_store* psi_store,
                               double* divT /* 2*Nt */);

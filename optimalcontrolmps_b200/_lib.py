@@ -20,7 +20,7 @@ SYMBOLS = [
     "ocmps_stepper_create", "ocmps_stepper_destroy", "ocmps_stepper_set_tstep", "ocmps_stepper_get_tstep",
     "ocmps_step", "ocmps_apply_K", "ocmps_stepper_schedule", "ocmps_stepper_gate",
     "ocmps_store_create", "ocmps_store_destroy", "ocmps_store_get", "ocmps_store_put", "ocmps_store_bond_dims",
-    "ocmps_forward_sweep", "ocmps_backward_sweep", "ocmps_sweep_pair", "ocmps_backward_sweep_divT",
+    "ocmps_forward_sweep", "ocmps_backward_sweep", "ocmps_sweep_pair", "ocmps_sweep_batch", "ocmps_backward_sweep_divT",
     "ocmps_store_overlaps", "ocmps_store_divT", "ocmps_store_apply_K", "ocmps_hessian_rows",
 ]
 
@@ -78,6 +78,7 @@ def load():
         "ocmps_forward_sweep": (i, [vp, vp, pd, i, vp]),
         "ocmps_backward_sweep": (i, [vp, vp, pd, i, vp]),
         "ocmps_sweep_pair": (i, [vp, vp, vp, pd, i, vp, vp]),
+        "ocmps_sweep_batch": (i, [vp, i, pvp, pi, pd, i, pvp]),
         "ocmps_backward_sweep_divT": (i, [vp, vp, pd, i, vp, pd]),
         "ocmps_store_overlaps": (i, [vp, vp, i, pd]),
         "ocmps_store_divT": (i, [vp, vp, i, pd]),

@@ -710,3 +710,40 @@ class OptimalControl:
         if self.GRAPE:
             return np.eye(self.N).tolist()
         return self.basis.getControlJacobian()
+
+
+def batch_cost_gradient(problems: Sequence["OptimalControl"], controls: Sequence[Sequence[float]]):
+    """Cost and analytic gradient of several independent controls at once on one GPU (batched seeds of the north
+    star).  ``problems[k]`` evaluates ``controls[k]``; all problems share one stepper and are in non-BFGS mode.  The
+    2*len(problems) sweeps run concurrently on their own streams (``ocmps_sweep_batch``); each problem ends in exactly
+    the state ``getAnalyticGradient(c, True); getCost(c, False)`` leaves it in.  Returns [(cost, gradient), ...]."""
+    assert len(problems) == len(controls) and len(problems) >= 1
+    st = problems[0].timeStepper
+    N = problems[0].N
+    us, starts, fwd, stores = [], [], [], []
+    for p, c in zip(problems, controls):
+        assert p.timeStepper is st and p.N == N and not p.BFGS
+        u = np.ascontiguousarray(c if p.GRAPE else p.basis.convertControl(c, True), dtype=np.float64)
+        assert u.size == N
+        us += [u, u]
+        starts += [p.psi_init.h, p.psi_target.h]
+        fwd += [1, 0]
+        stores += [p.psi_t.h, p.xi_t.h]
+    n = len(starts)
+    U = np.ascontiguousarray(np.stack(us))
+    a_starts = (C.c_void_p * n)(*starts)
+    a_stores = (C.c_void_p * n)(*stores)
+    a_fwd = np.array(fwd, dtype=np.int32)
+    _lib.check(st.ctx.lib.ocmps_sweep_batch(st.h, n, a_starts, _pi(a_fwd), _pd(U), N, a_stores))
+    out = []
+    for k, (p, c) in enumerate(zip(problems, controls)):
+        u = us[2 * k]
+        p.calculatedXi = True
+        p._calcDivT()
+        of = p._overlapFactor()
+        fg = [p.tstep * (p.divT[i] * of * 1j).real for i in range(N)]
+        g = [x + y for x, y in zip(fg, p._calcRegularizationGrad(u))]
+        ov = p._fid_ovl[-1]
+        cost = 0.5 * (1.0 - (ov.real * ov.real + ov.imag * ov.imag)) + p._calcRegularization(u)
+        out.append((cost, g if p.GRAPE else p.basis.convertGradient(g)))
+    return out

@@ -1108,6 +1108,46 @@ int ocmps_sweep_pair(ocmps_stepper* st, ocmps_mps* psi_init, ocmps_mps* psi_targ
   return check_status(st->ctx);
 }
 
+int ocmps_sweep_batch(ocmps_stepper* st, int nchains, ocmps_mps** starts, const int* forward, const double* u, int Nt,
+                      ocmps_store** stores) {
+  if (!st || !starts || !forward || !u || !stores || nchains < 1) return fail(OCMPS_ERR_INVALID, "bad argument");
+  int rc = OCMPS_OK;
+  for (int c = 0; c < nchains; ++c) {
+    rc = sweep_args_ok(st, starts[c], u + (size_t)c * Nt, Nt, stores[c]);
+    if (rc) return rc;
+    if (!stores[c]) return fail(OCMPS_ERR_INVALID, "null store");
+  }
+  CK(cudaSetDevice(st->ctx->dev));
+  std::vector<Workspace*> wss(nchains);
+  for (int c = 0; c < nchains; ++c) {
+    rc = get_ws(st->ctx, st->L, st->D, st->cap, c, &wss[c]);
+    if (rc) return rc;
+  }
+  CK(cudaDeviceSynchronize());
+  for (int c = 0; c < nchains; ++c) {
+    rc = sweep_enqueue_init(st, wss[c], starts[c], stores[c], forward[c] ? 0 : Nt - 1);
+    if (rc) return rc;
+  }
+  for (int k = 0; k < Nt - 1; ++k) {          // all chains advance in lock step so every stream stays fed
+    for (int c = 0; c < nchains; ++c) {
+      const double* uc = u + (size_t)c * Nt;
+      Workspace* ws = wss[c];
+      if (forward[c]) {
+        run_step(st, ws->work, ws, uc[k], uc[k + 1], true, ws->stream);
+        rc = store_put_async(stores[c], k + 1, ws->work, ws->stream);
+      } else {
+        const int i = Nt - 1 - k;
+        run_step(st, ws->work, ws, uc[i], uc[i - 1], false, ws->stream);
+        rc = store_put_async(stores[c], i - 1, ws->work, ws->stream);
+      }
+      if (rc) return rc;
+    }
+  }
+  CK(cudaDeviceSynchronize());
+  CK(cudaGetLastError());
+  return check_status(st->ctx);
+}
+
 int ocmps_backward_sweep_divT(ocmps_stepper* st, ocmps_mps* psi_target, const double* u, int Nt, ocmps_store* psi_store,
                               double* divT) {
   int rc = sweep_args_ok(st, psi_target, u, Nt, psi_store);

@@ -218,3 +218,27 @@ def test_edge_cases():
         st = make_stepper(oc, L, 2, 1.0, 1e-2, 1e-10, None)
         gates = [(op[1], op[1] + 1) for op in st.schedule() if op[0] == 1]
         assert gates == ob.gate_order(L)
+
+
+def test_batched_controls_match_single_evaluations(golden):
+    """ocmps_sweep_batch: several independent controls in flight on one GPU give exactly the single-evaluation results."""
+    g = golden
+    oc, z, st, N, M = g["oc"], g["z"], g["st"], g["N"], g["M"]
+    u0 = oc.SeedGenerator.linspace(g["cs"], g["ce"], N)
+    rng = np.random.default_rng(77)
+    probs, ctrls = [], []
+    for k in range(3):
+        basis = oc.ControlBasisFactory.buildChoppedSineBasis(u0, g["ts"], g["T"], M)
+        probs.append(oc.OptimalControl(to_host(g["target"]), to_host(g["init"]), st, basis, g["gamma"]))
+        ctrls.append(list(rng.uniform(-1, 1, M)))
+    ctrls[0] = list(z["c"])
+    res = oc.batch_cost_gradient(probs, ctrls)
+    assert abs(res[0][0] - float(z["group_cost"])) / abs(float(z["group_cost"])) < TOL_COST
+    assert rel(res[0][1], z["group_grad"]) < TOL_GRAD
+    for k in range(3):
+        single = oc.OptimalControl(to_host(g["target"]), to_host(g["init"]), st, probs[k].basis, g["gamma"])
+        gs = single.getAnalyticGradient(ctrls[k], True)
+        cs = single.getCost(ctrls[k], False)
+        assert abs(cs - res[k][0]) < 1e-12
+        assert np.max(np.abs(np.array(gs) - np.array(res[k][1]))) < 1e-12
+        assert abs(probs[k].getCost(ctrls[k], False) - cs) < 1e-12       # the problem is left in the cached state
