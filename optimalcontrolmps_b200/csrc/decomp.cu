@@ -835,6 +835,8 @@ static bool g_prof_on = false;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 static size_t g_prof_used = 0;
 
+bool profile_is_on() { return g_prof_on; }
+
 void profile_enable(bool on) {
   g_prof_on = on;
   g_prof_used = 0;

@@ -29,10 +29,20 @@ __global__ void merge_setup_kernel(GemmDesc* d, const cplx* A1, const cplx* A2, 
 template <int D>
 __global__ void __launch_bounds__(128) gate_apply_kernel(cplx* __restrict__ theta, const int* dimL, const int* dimR,
                                                         const int* __restrict__ qL, const int* __restrict__ qR,
-                                                        const cplx* __restrict__ G, Phases ph) {
+                                                        const StepParams* __restrict__ sp, int gate_kind) {
   extern __shared__ __align__(16) unsigned char gate_smem[];
+  __shared__ Phases ph;
   cplx* W = reinterpret_cast<cplx*>(gate_smem);
   const int chiL = *dimL, chiR = *dimR;
+  const cplx* __restrict__ G = sp->G;
+  if (threadIdx.x < D) {                       // [0],[1]: phases before the J gate on site 1, 2; [2],[3]: after it
+    const int n = threadIdx.x;
+    const bool pre = gate_kind != 2;
+    ph.re[0][n] = ph.re[1][n] = pre ? sp->u1r[n] : 1.0; ph.im[0][n] = ph.im[1][n] = pre ? sp->u1i[n] : 0.0;
+    ph.re[2][n] = gate_kind == 2 ? sp->u2r[n] : 1.0;     ph.im[2][n] = gate_kind == 2 ? sp->u2i[n] : 0.0;
+    ph.re[3][n] = gate_kind != 0 ? sp->u2r[n] : 1.0;     ph.im[3][n] = gate_kind != 0 ? sp->u2i[n] : 0.0;
+  }
+  __syncthreads();
   for (int e = threadIdx.x; e < D * D * D * D; e += blockDim.x) {
     const int row = e / (D * D), col = e % (D * D);
     const int t1 = row / D, t2 = row % D, s1 = col / D, s2 = col % D;
@@ -79,14 +89,34 @@ __global__ void __launch_bounds__(128) gate_apply_kernel(cplx* __restrict__ thet
   }
 }
 
-__global__ void site_phase_kernel(cplx* A, const int* dimL, const int* dimR, int D, Phases ph, int which) {
+__global__ void site_phase_kernel(cplx* A, const int* dimL, const int* dimR, int D, const StepParams* __restrict__ sp, int which) {
   const int chiL = *dimL, chiR = *dimR;
   const long long total = (long long)chiL * D * chiR;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int s = (int)((e / chiR) % D);
     const cplx u = A[e];
-    const double pr = ph.re[which][s], pi = ph.im[which][s];
+    const double pr = which == 0 ? sp->u1r[s] : sp->u2r[s], pi = which == 0 ? sp->u1i[s] : sp->u2i[s];
     A[e] = make_double2(u.x * pr - u.y * pi, u.x * pi + u.y * pr);
+  }
+}
+
+__global__ void set_step_params_kernel(StepParams hp, StepParams* dst) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *dst = hp;
+}
+
+// work MPS -> store slot named by *sp; blockIdx.y = site, the last y-slice copies dims and charge labels
+__global__ void pack_to_slot_kernel(SitePtrs src, SiteOffs offs, const int* dims, const int* q, int L, int D, int cap,
+                                    const StepParams* __restrict__ sp) {
+  const int j = blockIdx.y;
+  if (j < L) {
+    const long long count = (long long)dims[j] * D * dims[j + 1];
+    const cplx* s = src.p[j];
+    cplx* d = sp->slot_data + offs.o[j];
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x) d[e] = s[e];
+  } else {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int b = tid; b <= L; b += nt) sp->slot_dims[b] = dims[b];
+    for (int e = tid; e < (L + 1) * cap; e += nt) sp->slot_q[e] = q[e];
   }
 }
 
@@ -212,8 +242,8 @@ void launch_merge_setup(GemmDesc* d, const cplx* A1, const cplx* A2, cplx* theta
   merge_setup_kernel<<<1, 32, 0, s>>>(d, A1, A2, theta, dimL, dimM, dimR, D);
 }
 
-void launch_gate_apply(cplx* theta, const int* dimL, const int* dimR, const int* qL, const int* qR, int D, const cplx* G, Phases ph,
-                       int maxL, int maxR, cudaStream_t s) {
+void launch_gate_apply(cplx* theta, const int* dimL, const int* dimR, const int* qL, const int* qR, int D, const StepParams* sp,
+                       int gate_kind, int maxL, int maxR, cudaStream_t s) {
   const int grid = grid_for((long long)maxL * maxR, 128);
   const size_t sm = sizeof(cplx) * D * D * D * D;
   static bool attr8 = false;
@@ -222,19 +252,29 @@ void launch_gate_apply(cplx* theta, const int* dimL, const int* dimR, const int*
     attr8 = true;
   }
   switch (D) {
-    case 2: gate_apply_kernel<2><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, G, ph); break;
-    case 3: gate_apply_kernel<3><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, G, ph); break;
-    case 4: gate_apply_kernel<4><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, G, ph); break;
-    case 5: gate_apply_kernel<5><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, G, ph); break;
-    case 6: gate_apply_kernel<6><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, G, ph); break;
-    case 7: gate_apply_kernel<7><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, G, ph); break;
-    case 8: gate_apply_kernel<8><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, G, ph); break;
+    case 2: gate_apply_kernel<2><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, sp, gate_kind); break;
+    case 3: gate_apply_kernel<3><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, sp, gate_kind); break;
+    case 4: gate_apply_kernel<4><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, sp, gate_kind); break;
+    case 5: gate_apply_kernel<5><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, sp, gate_kind); break;
+    case 6: gate_apply_kernel<6><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, sp, gate_kind); break;
+    case 7: gate_apply_kernel<7><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, sp, gate_kind); break;
+    case 8: gate_apply_kernel<8><<<grid, 128, sm, s>>>(theta, dimL, dimR, qL, qR, sp, gate_kind); break;
     default: break;
   }
 }
 
-void launch_site_phase(cplx* A, const int* dimL, const int* dimR, int D, Phases ph, int which, int max_elems, cudaStream_t s) {
-  site_phase_kernel<<<grid_for(max_elems, 256), 256, 0, s>>>(A, dimL, dimR, D, ph, which);
+void launch_site_phase(cplx* A, const int* dimL, const int* dimR, int D, const StepParams* sp, int which, int max_elems, cudaStream_t s) {
+  site_phase_kernel<<<grid_for(max_elems, 256), 256, 0, s>>>(A, dimL, dimR, D, sp, which);
+}
+
+void launch_set_step_params(const StepParams& hp, StepParams* dst, cudaStream_t s) {
+  set_step_params_kernel<<<1, 32, 0, s>>>(hp, dst);
+}
+
+void launch_pack_to_slot(SitePtrs src, SiteOffs offs, const int* dims, const int* q, int L, int D, int cap, int max_site_elems,
+                         const StepParams* sp, cudaStream_t s) {
+  dim3 grid(grid_for(max_site_elems, 256, 64), L + 1);
+  pack_to_slot_kernel<<<grid, 256, 0, s>>>(src, offs, dims, q, L, D, cap, sp);
 }
 
 void launch_pack_copy(SitePtrs src, cplx* dst_base, SiteOffs offs, const int* dims, int L, int D, int max_site_elems,

@@ -14,7 +14,9 @@
 #include <algorithm>
 #include <string>
 #include <atomic>
+#include <map>
 #include <mutex>
+#include <tuple>
 #include <thread>
 #include <vector>
 
@@ -136,6 +138,11 @@ struct Workspace {
   ocmps_mps* big = nullptr;    // 2*cap bonds, for K|psi>
   Workspace* bigws = nullptr;  // decomposition buffers for 2*cap
   double* d_norm = nullptr;    // scalar outputs
+  StepParams* d_params = nullptr;   // per-step scalars and pointers (device), see StepParams
+  ocmps_mps* psiH = nullptr;        // Hessian-row state of this chain
+  // CUDA graphs of one Trotter step (+ slice store), keyed by stepper serial, MPS buffers, buffer parity, with/without store
+  struct StepGraph { cudaGraphExec_t exec = nullptr; unsigned long long flips = 0; int launches = 0; int seen = 0; };
+  std::map<std::tuple<long long, const void*, unsigned long long, int>, StepGraph> graphs;
 };
 
 struct ocmps_stepper {
@@ -149,6 +156,7 @@ struct ocmps_stepper {
   cplx* d_G[2] = {nullptr, nullptr};     // [0] forward, [1] backward
   std::vector<std::complex<double>> h_G[2];
   std::vector<Op> ops;
+  long long serial = 0;      // unique id (graph cache key)
 };
 
 namespace {
@@ -205,6 +213,7 @@ int alloc_ws(ocmps_ctx* ctx, int L, int D, int cap, bool with_work, Workspace** 
   CK(cudaMalloc(&w->db.descs, sizeof(GemmDesc) * 4));
   CK(cudaMalloc(&w->db.partial, sizeof(double) * 64));
   CK(cudaMalloc(&w->d_norm, sizeof(double) * 4));
+  CK(cudaMalloc(&w->d_params, sizeof(StepParams)));
   w->db.status = ctx->d_status;
   if (with_work) {
     int rc = alloc_mps(ctx, L, D, cap, &w->work);
@@ -232,7 +241,9 @@ void free_ws(Workspace* w) {
   if (!w) return;
   cudaFree(w->theta); cudaFree(w->cbuf); cudaFree(w->db.dw); cudaFree(w->db.vec_idx); cudaFree(w->db.comp_idx);
   cudaFree(w->db.vecq); cudaFree(w->db.P); cudaFree(w->db.pos); cudaFree(w->db.ywork); cudaFree(w->db.descs);
-  cudaFree(w->db.partial); cudaFree(w->d_norm); cudaFree(w->db.scratch_d);
+  cudaFree(w->db.partial); cudaFree(w->d_norm); cudaFree(w->db.scratch_d); cudaFree(w->d_params);
+  for (auto& kv : w->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  free_mps(w->psiH);
   cudaFree(w->E[0]); cudaFree(w->E[1]); cudaFree(w->T); cudaFree(w->odescs); cudaFree(w->d_out);
   free_mps(w->work); free_mps(w->big);
   if (w->bigws) free_ws(w->bigws);
@@ -403,15 +414,11 @@ void phases_of(int D, double U, double tstep, double* re, double* im) {
   }
 }
 
-// one Trotter step in place on `m`, enqueued on `s`
-void run_step(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, double from, double to, bool forward, cudaStream_t s,
-              int op_begin = 0, int op_end = 1 << 30) {
+// the kernel sequence of one Trotter step in place on `m` (all step-dependent values are read from ws->d_params)
+void run_step_body(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, cudaStream_t s, int op_begin = 0, int op_end = 1 << 30) {
   const int L = st->L, D = st->D;
   const Layout& lay = m->lay;
-  double u1r[OCMPS_MAX_D], u1i[OCMPS_MAX_D], u2r[OCMPS_MAX_D], u2i[OCMPS_MAX_D];
-  phases_of(D, forward ? from : -from, st->tstep, u1r, u1i);   // :116-123
-  phases_of(D, forward ? to : -to, st->tstep, u2r, u2i);
-  const cplx* G = st->d_G[forward ? 0 : 1];
+  const StepParams* sp = ws->d_params;
   TruncParams tpg{st->cutoff, st->maxm, 1, st->rel_cutoff, 0, 1};
   TruncParams tpo{MIN_CUT, MAX_M, 1, 0, 0, 0};
 
@@ -419,29 +426,15 @@ void run_step(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, double from, doubl
     const Op& op = st->ops[oi];
     if (op.kind == 0) {
       const int j = op.a - 1;
-      Phases ph;
-      for (int n = 0; n < D; ++n) {
-        ph.re[0][n] = op.b == 0 ? u1r[n] : u2r[n];
-        ph.im[0][n] = op.b == 0 ? u1i[n] : u2i[n];
-      }
-      launch_site_phase(m->site(j), m->dim(j), m->dim(j + 1), D, ph, 0, lay.capb[j] * D * lay.capb[j + 1], s);
+      launch_site_phase(m->site(j), m->dim(j), m->dim(j + 1), D, sp, op.b, lay.capb[j] * D * lay.capb[j + 1], s);
       g_ocmps_launches += 1;
     } else if (op.kind == 1) {
       const int j1 = op.a - 1, j2 = op.a;                 // 0-based sites
       const int bl = j1, bm = j1 + 1, br = j2 + 1;        // bonds
       launch_merge_setup(ws->db.descs + 2, m->site(j1), m->site(j2), ws->theta, m->dim(bl), m->dim(bm), m->dim(br), D, s);
       launch_zgemm(ws->db.descs + 2, 1, lay.capb[bl] * D, D * lay.capb[br], s);
-      Phases ph;
-      for (int n = 0; n < D; ++n) {
-        for (int k = 0; k < 4; ++k) { ph.re[k][n] = 1.0; ph.im[k][n] = 0.0; }
-        if (op.b == 0 || op.b == 1) {                       // U(from) before the J gate (:150)
-          ph.re[0][n] = ph.re[1][n] = u1r[n]; ph.im[0][n] = ph.im[1][n] = u1i[n];
-          if (op.b == 1) { ph.re[3][n] = u2r[n]; ph.im[3][n] = u2i[n]; }   // lonely U(to) on the last site (:153-155)
-        } else {                                            // J gate first, then U(to) (:159)
-          ph.re[2][n] = ph.re[3][n] = u2r[n]; ph.im[2][n] = ph.im[3][n] = u2i[n];
-        }
-      }
-      launch_gate_apply(ws->theta, m->dim(bl), m->dim(br), m->q(bl), m->q(br), D, G, ph, lay.capb[bl], lay.capb[br], s);
+      // op.b: 0 = U(from) then J (:150), 1 = plus the lonely U(to) on the last site (:153-155), 2 = J then U(to) (:159)
+      launch_gate_apply(ws->theta, m->dim(bl), m->dim(br), m->q(bl), m->q(br), D, sp, op.b, lay.capb[bl], lay.capb[br], s);
       DecompArgs a;
       a.kind = op.c == 0 ? DK_GATE_LEFT : DK_GATE_RIGHT;
       a.D = D;
@@ -494,6 +487,87 @@ void run_step(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, double from, doubl
     }
   }
   if (op_end >= (int)st->ops.size()) { m->llim = 0; m->rlim = 2; }
+}
+
+void fill_step_params(ocmps_stepper* st, double from, double to, bool forward, ocmps_store* store, int slot, StepParams& hp) {
+  phases_of(st->D, forward ? from : -from, st->tstep, hp.u1r, hp.u1i);   // src/BH_tDMRG.cpp:116-123
+  phases_of(st->D, forward ? to : -to, st->tstep, hp.u2r, hp.u2i);
+  hp.G = st->d_G[forward ? 0 : 1];
+  hp.slot_data = nullptr; hp.slot_dims = nullptr; hp.slot_q = nullptr;
+  if (store) {
+    const Layout& lay = store->lay;
+    hp.slot_data = store->data + (size_t)slot * lay.total;
+    hp.slot_dims = store->dims + (size_t)slot * (lay.L + 1);
+    hp.slot_q = store->q + (size_t)slot * (lay.L + 1) * lay.cap;
+  }
+}
+
+static bool graphs_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("OCMPS_GRAPH"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+// One Trotter step in place on `m` (and, if `store` is given, the copy of the result into `slot`), enqueued on `s`.
+// The kernel sequence only depends on (stepper, MPS buffers, buffer parity): after one plain execution it is captured
+// into a CUDA graph and replayed -- 1 graph launch + 1 parameter kernel instead of ~230 launches per step.
+int step_enqueue(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, double from, double to, bool forward, ocmps_store* store, int slot,
+                 cudaStream_t s) {
+  if (store) {
+    const Layout& lay = store->lay;
+    if (m->lay.L != lay.L || m->lay.D != lay.D || m->lay.cap != lay.cap) return fail(OCMPS_ERR_INVALID, "store/mps shape mismatch");
+    if (slot < 0 || slot >= store->nslots) return fail(OCMPS_ERR_INVALID, "slot out of range");
+  }
+  StepParams hp;
+  fill_step_params(st, from, to, forward, store, slot, hp);
+  launch_set_step_params(hp, ws->d_params, s);
+  g_ocmps_launches += 1;
+  const Layout& lay = m->lay;
+  auto body = [&]() {
+    run_step_body(st, m, ws, s);
+    if (store) {
+      launch_pack_to_slot(m->ptrs(), lay.offs, m->d_dims, m->d_q, lay.L, lay.D, lay.cap, lay.max_site_elems, ws->d_params, s);
+      g_ocmps_launches += 1;
+    }
+  };
+  if (!graphs_enabled() || profile_is_on()) { body(); return OCMPS_OK; }   // event timing needs plain launches
+  unsigned long long parity = 0;
+  for (int j = 0; j < lay.L; ++j) parity |= (unsigned long long)(m->cur[j] & 1) << j;
+  auto key = std::make_tuple(st->serial, (const void*)m->arena[0], parity, store ? 1 : 0);
+  Workspace::StepGraph& g = ws->graphs[key];
+  if (g.exec) {
+    for (int j = 0; j < lay.L; ++j) m->cur[j] ^= (int)((g.flips >> j) & 1ull);
+    m->llim = 0; m->rlim = 2;
+    g_ocmps_launches += g.launches;
+    CK(cudaGraphLaunch(g.exec, s));
+    return OCMPS_OK;
+  }
+  if (g.seen == 0) {            // first use: plain launches (also sets the function attributes the kernels need)
+    g.seen = 1;
+    body();
+    return OCMPS_OK;
+  }
+  if (ws->graphs.size() > 64) {   // stale entries (freed MPS buffers): start over
+    for (auto& kv : ws->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    ws->graphs.clear();
+    Workspace::StepGraph& g2 = ws->graphs[key];
+    g2.seen = 1;
+    body();
+    return OCMPS_OK;
+  }
+  const long long l0 = g_ocmps_launches;
+  cudaGraph_t graph = nullptr;
+  CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+  body();
+  CK(cudaStreamEndCapture(s, &graph));
+  unsigned long long after = 0;
+  for (int j = 0; j < lay.L; ++j) after |= (unsigned long long)(m->cur[j] & 1) << j;
+  g.flips = parity ^ after;
+  g.launches = (int)(g_ocmps_launches - l0);
+  CK(cudaGraphInstantiate(&g.exec, graph, 0));
+  CK(cudaGraphDestroy(graph));
+  CK(cudaGraphLaunch(g.exec, s));
+  return OCMPS_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -873,6 +947,7 @@ int ocmps_stepper_create(ocmps_ctx* ctx, int L, int D, double J, double tstep, d
   st->has_maxm = maxm > 0; st->maxm = st->has_maxm ? maxm : MAX_M;
   st->rel_cutoff = rel_cutoff ? 1 : 0;
   st->ops = build_schedule(L);
+  { static std::atomic<long long> next_serial{1}; st->serial = next_serial++; }
   int rc = ocmps_stepper_set_tstep(st, tstep);
   if (rc) { delete st; return rc; }
   *out = st;
@@ -922,7 +997,8 @@ int ocmps_step(ocmps_stepper* st, ocmps_mps* psi, double from, double to, int fo
   rc = get_ws(st->ctx, st->L, st->D, st->cap, 0, &ws);
   if (rc) return rc;
   CK(cudaDeviceSynchronize());
-  run_step(st, psi, ws, from, to, forward != 0, ws->stream);
+  rc = step_enqueue(st, psi, ws, from, to, forward != 0, nullptr, 0, ws->stream);
+  if (rc) return rc;
   CK(cudaStreamSynchronize(ws->stream));
   CK(cudaGetLastError());
   return check_status(st->ctx);
@@ -937,7 +1013,8 @@ int ocmps_debug_run_ops(ocmps_stepper* st, ocmps_mps* psi, double from, double t
   int rc = get_ws(st->ctx, st->L, st->D, st->cap, 0, &ws);
   if (rc) return rc;
   CK(cudaDeviceSynchronize());
-  run_step(st, psi, ws, from, to, forward != 0, ws->stream, op_begin, op_end);
+  { StepParams hp; fill_step_params(st, from, to, forward != 0, nullptr, 0, hp); launch_set_step_params(hp, ws->d_params, ws->stream); }
+  run_step_body(st, psi, ws, ws->stream, op_begin, op_end);
   CK(cudaStreamSynchronize(ws->stream));
   CK(cudaGetLastError());
   return check_status(st->ctx);
@@ -1045,8 +1122,7 @@ int ocmps_forward_sweep(ocmps_stepper* st, ocmps_mps* psi_init, const double* u,
   rc = sweep_enqueue_init(st, ws, psi_init, store, 0);
   if (rc) return rc;
   for (int i = 0; i < Nt - 1; ++i) {
-    run_step(st, ws->work, ws, u[i], u[i + 1], true, ws->stream);
-    rc = store_put_async(store, i + 1, ws->work, ws->stream);
+    rc = step_enqueue(st, ws->work, ws, u[i], u[i + 1], true, store, i + 1, ws->stream);
     if (rc) return rc;
   }
   CK(cudaStreamSynchronize(ws->stream));
@@ -1066,8 +1142,7 @@ int ocmps_backward_sweep(ocmps_stepper* st, ocmps_mps* psi_target, const double*
   rc = sweep_enqueue_init(st, ws, psi_target, store, Nt - 1);
   if (rc) return rc;
   for (int i = Nt - 1; i > 0; --i) {
-    run_step(st, ws->work, ws, u[i], u[i - 1], false, ws->stream);
-    rc = store_put_async(store, i - 1, ws->work, ws->stream);
+    rc = step_enqueue(st, ws->work, ws, u[i], u[i - 1], false, store, i - 1, ws->stream);
     if (rc) return rc;
   }
   CK(cudaStreamSynchronize(ws->stream));
@@ -1094,12 +1169,10 @@ int ocmps_sweep_pair(ocmps_stepper* st, ocmps_mps* psi_init, ocmps_mps* psi_targ
   rc = sweep_enqueue_init(st, wb, psi_target, xi_store, Nt - 1);
   if (rc) return rc;
   for (int k = 0; k < Nt - 1; ++k) {      // interleave the two chains so both streams stay fed
-    run_step(st, wa->work, wa, u[k], u[k + 1], true, wa->stream);
-    rc = store_put_async(psi_store, k + 1, wa->work, wa->stream);
+    rc = step_enqueue(st, wa->work, wa, u[k], u[k + 1], true, psi_store, k + 1, wa->stream);
     if (rc) return rc;
     const int i = Nt - 1 - k;
-    run_step(st, wb->work, wb, u[i], u[i - 1], false, wb->stream);
-    rc = store_put_async(xi_store, i - 1, wb->work, wb->stream);
+    rc = step_enqueue(st, wb->work, wb, u[i], u[i - 1], false, xi_store, i - 1, wb->stream);
     if (rc) return rc;
   }
   CK(cudaStreamSynchronize(wa->stream));
@@ -1133,12 +1206,10 @@ int ocmps_sweep_batch(ocmps_stepper* st, int nchains, ocmps_mps** starts, const 
       const double* uc = u + (size_t)c * Nt;
       Workspace* ws = wss[c];
       if (forward[c]) {
-        run_step(st, ws->work, ws, uc[k], uc[k + 1], true, ws->stream);
-        rc = store_put_async(stores[c], k + 1, ws->work, ws->stream);
+        rc = step_enqueue(st, ws->work, ws, uc[k], uc[k + 1], true, stores[c], k + 1, ws->stream);
       } else {
         const int i = Nt - 1 - k;
-        run_step(st, ws->work, ws, uc[i], uc[i - 1], false, ws->stream);
-        rc = store_put_async(stores[c], i - 1, ws->work, ws->stream);
+        rc = step_enqueue(st, ws->work, ws, uc[i], uc[i - 1], false, stores[c], i - 1, ws->stream);
       }
       if (rc) return rc;
     }
@@ -1166,7 +1237,7 @@ int ocmps_backward_sweep_divT(ocmps_stepper* st, ocmps_mps* psi_target, const do
     rc = overlaps_async(ws, side_of_mps(ws->work), ws->work->lay, side_of_store(psi_store, i), psi_store->lay, 1, 1, ws->stream);
     if (rc) { cudaFree(d_div); return rc; }
     CK(cudaMemcpyAsync(d_div + i, ws->d_out, sizeof(cplx), cudaMemcpyDeviceToDevice, ws->stream));
-    if (i > 0) run_step(st, ws->work, ws, u[i], u[i - 1], false, ws->stream);
+    if (i > 0) { rc = step_enqueue(st, ws->work, ws, u[i], u[i - 1], false, nullptr, 0, ws->stream); if (rc) { cudaFree(d_div); return rc; } }
   }
   CK(cudaMemcpyAsync(divT, d_div, sizeof(cplx) * Nt, cudaMemcpyDeviceToHost, ws->stream));
   CK(cudaStreamSynchronize(ws->stream));
@@ -1252,8 +1323,11 @@ int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* x
   for (int c = 0; c < nchains; ++c) {
     rc = get_ws(st->ctx, st->L, st->D, st->cap, c, &wss[c]);
     if (rc) return rc;
-    rc = alloc_mps(st->ctx, st->L, st->D, st->cap, &psiH[c]);
-    if (rc) return rc;
+    if (!wss[c]->psiH) {          // kept with the workspace so that its step graphs stay valid across calls
+      rc = alloc_mps(st->ctx, st->L, st->D, st->cap, &wss[c]->psiH);
+      if (rc) return rc;
+    }
+    psiH[c] = wss[c]->psiH;
   }
   cplx* d_ovl = nullptr;
   double* d_norms = nullptr;
@@ -1307,7 +1381,8 @@ int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* x
         } else {
           if (S.j >= Nt - 1) { S.row = -1; busy = true; continue; }
           // one step forward and the overlap with xiH_j (:267-277)
-          run_step(st, psiH[c], ws, u[S.j - 1], u[S.j], true, ws->stream);
+          lrc = step_enqueue(st, psiH[c], ws, u[S.j - 1], u[S.j], true, nullptr, 0, ws->stream);
+          if (lrc) break;
           lrc = overlaps_async(ws, side_of_store(xiH_store, S.j), xiH_store->lay, side_of_mps(psiH[c]), psiH[c]->lay, 1, 0, ws->stream);
           if (lrc) break;
           if (cudaMemcpyAsync(d_ovl + (size_t)S.row * Nt + S.j, ws->d_out, sizeof(cplx), cudaMemcpyDeviceToDevice, ws->stream) != cudaSuccess) {
@@ -1338,7 +1413,6 @@ int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* x
     cudaMemcpy(norms, d_norms, sizeof(double) * Nt, cudaMemcpyDeviceToHost);
   }
   cudaFree(d_ovl); cudaFree(d_norms);
-  for (int c = 0; c < nchains; ++c) free_mps(psiH[c]);
   if (rc) return rc;
   CK(cudaGetLastError());
   return check_status(st->ctx);

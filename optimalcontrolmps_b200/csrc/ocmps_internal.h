@@ -54,6 +54,15 @@ struct TruncParams {
   int normalize;            // divide the centre-carrying factor by its Frobenius norm (src/BH_tDMRG.cpp:183-184)
 };
 
+// Everything that changes from one Trotter step to the next lives in device memory, so that the kernel sequence
+// of a step has constant arguments and can be replayed as a CUDA graph.
+struct StepParams {
+  double u1r[OCMPS_MAX_D], u1i[OCMPS_MAX_D];   // exp(-i/4 U_from tstep n(n-1))   (src/BH_tDMRG.cpp:84-88)
+  double u2r[OCMPS_MAX_D], u2i[OCMPS_MAX_D];   // ... U_to
+  const cplx* G;                               // forward or backward J gate
+  cplx* slot_data; int* slot_dims; int* slot_q; // destination slice of the store (or null)
+};
+
 struct SitePtrs { cplx* p[OCMPS_MAX_L]; };
 struct SiteOffs { long long o[OCMPS_MAX_L + 1]; };
 
@@ -65,6 +74,7 @@ extern std::atomic<long long> g_ocmps_launches;   // kernels launched so far (be
 
 void debug_jacobi_counters(unsigned long long* out, bool reset);
 void profile_enable(bool on);
+bool profile_is_on();
 void profile_read(double* out);
 
 // ---- kernels (launchers) ----
@@ -112,9 +122,14 @@ void launch_build_factors(const DecompArgs& a, const DecompBuffers& b, int cap_k
 // merge setup: fills desc for theta = A1 (chil*D x chim) * A2 (chim x D*chir)
 void launch_merge_setup(GemmDesc* d, const cplx* A1, const cplx* A2, cplx* theta, const int* dimL, const int* dimM,
                         const int* dimR, int D, cudaStream_t s);
-void launch_gate_apply(cplx* theta, const int* dimL, const int* dimR, const int* qL, const int* qR, int D, const cplx* G, Phases ph,
-                       int maxL, int maxR, cudaStream_t s);
-void launch_site_phase(cplx* A, const int* dimL, const int* dimR, int D, Phases ph, int which, int max_elems, cudaStream_t s);
+// gate_kind: 0 = U(from) then J, 1 = same plus the lonely U(to) on the second site, 2 = J then U(to)
+void launch_gate_apply(cplx* theta, const int* dimL, const int* dimR, const int* qL, const int* qR, int D, const StepParams* sp,
+                       int gate_kind, int maxL, int maxR, cudaStream_t s);
+void launch_site_phase(cplx* A, const int* dimL, const int* dimR, int D, const StepParams* sp, int which, int max_elems, cudaStream_t s);
+void launch_set_step_params(const StepParams& hp, StepParams* dst, cudaStream_t s);
+// pack the work MPS into the store slot named by *sp (data, dims and charge labels)
+void launch_pack_to_slot(SitePtrs src, SiteOffs offs, const int* dims, const int* q, int L, int D, int cap, int max_site_elems,
+                         const StepParams* sp, cudaStream_t s);
 void launch_norm_only(const cplx* x, const int* dimL, const int* dimR, int D, double* partial, double* out, int max_elems,
                       cudaStream_t s);
 void launch_normalize_site(cplx* x, const int* dimL, const int* dimR, int D, double* partial, int max_elems, cudaStream_t s);
