@@ -78,6 +78,7 @@ struct ocmps_ctx {
   int dev = 0;
   int* d_status = nullptr;
   cudaStream_t stream0 = nullptr;
+  int qmax = 0;                 // largest boson-number label uploaded so far: bounds the number of charge blocks
   std::vector<struct Workspace*> pool;
 };
 
@@ -395,7 +396,9 @@ void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int c
   size_t need = (size_t)capV * capC * sizeof(cplx);
   size_t smem = std::min(need, JAC_SMEM_LIMIT);
   if (smem < 1024) smem = 1024;
-  int nblk = std::min(OCMPS_MAX_BLK, std::max(capV, capC) + a.D);
+  // blocks are labelled by a charge in [0, qmax + D): launch no more CTAs than that (surplus CTAs would still have to
+  // wait for an SM with the full shared-memory carve-out and would serialise concurrent chains)
+  int nblk = std::min(std::min(OCMPS_MAX_BLK, std::max(capV, capC) + a.D), ws->ctx->qmax + a.D + 1);
   const bool need_global = need > JAC_SMEM_LIMIT;    // some block may not fit in shared memory
   // numerical-rank tolerance of the pivoted QR: the neglected weight stays >= 6 orders below the cutoff
   double rank_tol = 1e-6 * tp.cutoff;
@@ -808,6 +811,7 @@ int ocmps_mps_upload(ocmps_mps* m, const int* bond_dims, const int* charges, con
       perm[b].resize(nb);
       for (int i = 0; i < nb; ++i) perm[b][i] = i;
       const int* qb = charges + qo;
+      for (int i = 0; i < nb; ++i) m->ctx->qmax = std::max(m->ctx->qmax, qb[i]);
       std::stable_sort(perm[b].begin(), perm[b].end(), [qb](int x, int y) { return qb[x] < qb[y]; });
       std::vector<int> sorted(nb);
       for (int i = 0; i < nb; ++i) sorted[i] = qb[perm[b][i]];
