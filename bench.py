@@ -71,7 +71,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.5)
 
     def summary(self):
         if not self.rows:
@@ -227,7 +227,10 @@ def run_ours(args):
     st = oc.BH_tDMRG(oc.BoseHubbard(L, d), CFG["J"], CFG["tstep"], oc.Args("Cutoff=", CFG["cutoff"], "Maxm=", CFG["maxm"]), ctx=ctx)
     psi_i = ground_state(L, d, CFG["Npart"], CFG["U_i"])
     psi_f = ground_state(L, d, CFG["Npart"], CFG["U_f"])
-    basis, c, u = make_problem_host(rank)          # every rank its own control (independent units)
+    # N>1: every rank evaluates one control on its own GPU (independent replicas; a single evaluation does not shard).
+    # By default all ranks use the same synthetic control so that the per-GPU work is identical (weak scaling);
+    # --distinct-seeds gives every rank its own control (evaluation times then differ by up to ~30 % between seeds).
+    basis, c, u = make_problem_host(rank if args.distinct_seeds else max(args.seed, 0))
     ocp = oc.OptimalControl(psi_f, psi_i, st, basis, CFG["gamma"])
     ocp.setThreadCount(2)                          # psi and xi sweeps on two streams (reference: 2 threads)
     N, M = nt(), CFG["M"]
@@ -240,7 +243,8 @@ def run_ours(args):
     for _ in range(args.warmup):
         one_eval()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -259,7 +263,8 @@ def run_ours(args):
     dev_ms = e0.elapsed_time(e1)
     launches = lib.ocmps_launch_count() - l0
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
     # max over ranks of the device-timed region and of the end-to-end wall clock
     tt = torch.tensor([dev_ms * 1e-3, wall], dtype=torch.float64, device=dev)
     if world > 1:
@@ -276,7 +281,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "complex128 (f64)", "data": "synthetic",
-            "config": {"workload": "cfg2: BH L=20 Npart=20 d=5 T=2.0 tstep=0.01 GROUP M=10 chi=100 single cost+gradient eval per GPU",
+            "config": {"workload": "cfg2: BH L=20 Npart=20 d=5 T=2.0 tstep=0.01 GROUP M=10 chi=100 single cost+gradient eval per GPU (N>1: independent replicas, one all-gather of the results)",
                        **CFG, "Nt": N, "l2": "inputs larger than L2: the two slice stores are rewritten every eval (5.7 GB capacity)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(8 * M + 8 * N), "d2h_bytes_per_step": int(8 * (1 + M) + 16 * 2 * N)},
             "gpu_launches": int(launches), "clocks": sampler.summary(),
@@ -380,6 +385,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--hessian-nt", type=int, default=0, help="additionally time a sharded GRAPE Hessian with this many time points")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=0, help="seed of the synthetic control")
+    ap.add_argument("--distinct-seeds", action="store_true", help="N>1: rank r evaluates the control of seed r")
     ap.add_argument("--batch", type=int, default=6, help="additionally time this many independent controls in flight on one GPU")
     args = ap.parse_args()
     if args.impl == "reference":
