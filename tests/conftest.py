@@ -51,3 +51,44 @@ def golden_state(z, prefix):
 
 def load_golden(name):
     return np.load(os.path.join(GOLDEN, name))
+
+
+def random_symmetric_mps(L, D, Npart, chi, seed):
+    """Random number-conserving MPS with bond dimensions up to ``chi`` (flat spectra: a stress input), canonical
+    with the centre at site 1.  Built with the oracle's containers."""
+    from oracle import bh_mps as ob
+    rng = np.random.default_rng(seed)
+    # number of left-half configurations per charge bounds the multiplicity of each label
+    ways = [np.zeros(Npart + 1, dtype=object) for _ in range(L + 1)]
+    ways[0][0] = 1
+    for b in range(1, L + 1):
+        for q in range(Npart + 1):
+            ways[b][q] = sum(ways[b - 1][q - s] for s in range(D) if 0 <= q - s)
+    waysR = [np.zeros(Npart + 1, dtype=object) for _ in range(L + 1)]
+    waysR[L][Npart] = 1
+    for b in range(L - 1, -1, -1):
+        for q in range(Npart + 1):
+            waysR[b][q] = sum(waysR[b + 1][q + s] for s in range(D) if q + s <= Npart)
+    qs = []
+    for b in range(L + 1):
+        cap = np.array([min(int(ways[b][q]), int(waysR[b][q])) for q in range(Npart + 1)])
+        allowed = np.nonzero(cap > 0)[0]
+        mult = np.zeros(Npart + 1, dtype=int)
+        want = min(chi, int(cap.sum()))
+        while mult.sum() < want:                     # round-robin fill, centre charges first
+            order = sorted(allowed, key=lambda q: abs(q - Npart * b / L))
+            for q in order:
+                if mult.sum() < want and mult[q] < cap[q]:
+                    mult[q] += 1
+        qs.append(np.repeat(np.arange(Npart + 1), mult).astype(np.int64))
+    A = []
+    s = np.arange(D)
+    for j in range(L):
+        ql, qr = qs[j], qs[j + 1]
+        a = rng.normal(size=(len(ql), D, len(qr))) + 1j * rng.normal(size=(len(ql), D, len(qr)))
+        ok = (ql[:, None, None] + s[None, :, None]) == qr[None, None, :]
+        A.append(a * ok)
+    psi = ob.MPS(A, qs, llim=0, rlim=L + 1)
+    psi.position(1)
+    psi.normalize()
+    return psi

@@ -66,3 +66,32 @@ def test_fast_ramp_properties(cfg2):
     got = to_oracle(last.download())
     assert got.bond_dims() == po.bond_dims()
     assert abs(abs(ob.overlap(po, got)) - 1.0) < 1e-10
+
+
+def test_large_blocks_beyond_shared_memory():
+    """Bond dimension 160 (> 128): charge blocks that do not fit the 200 KB shared-memory tile take the global-memory
+    variant of the block kernel, rows longer than 128 take the non-cached rotation path.  A random number-conserving
+    MPS has flat spectra, so Maxm binds at every bond and every block is large."""
+    import optimalcontrolmps_b200 as oc
+    from oracle import bh_mps as ob
+    from conftest import random_symmetric_mps
+    L, d, Np, chi = 10, 5, 10, 160
+    psi = random_symmetric_mps(L, d + 1, Np, chi, seed=5)
+    assert max(psi.bond_dims()) > 128
+    so = ob.BHStepper(L, d + 1, 1.0, 1e-2, ob.TruncArgs(cutoff=1e-10, maxm=chi))
+    st = oc.BH_tDMRG(oc.BoseHubbard(L, d), 1.0, 1e-2, oc.Args("Cutoff=", 1e-10, "Maxm=", chi))
+    dev = st.to_device(to_host(psi))
+    po = psi.copy()
+    for k in range(2):
+        so.step(po, 3.0 + k, 4.0 + k, True)
+        st.step(dev, 3.0 + k, 4.0 + k, True)
+        got = to_oracle(dev.download())
+        assert got.bond_dims() == po.bond_dims()
+        assert abs(abs(ob.overlap(po, got)) - 1.0) < 1e-10
+        assert got.check_charges() == 0.0
+    # K|psi> needs bonds of 2*chi = 320 inside: also through the global-memory variant
+    kg = to_oracle(st.exactApplyMPO(dev).download())
+    ko = ob.apply_K(po, ob.TruncArgs(cutoff=1e-10, maxm=chi))
+    assert kg.bond_dims() == ko.bond_dims()
+    assert abs(kg.norm() - ko.norm()) < 1e-9 * ko.norm()
+    assert abs(abs(ob.overlap(ko, kg)) / (ko.norm() * kg.norm()) - 1.0) < 1e-9
