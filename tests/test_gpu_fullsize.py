@@ -95,3 +95,29 @@ def test_large_blocks_beyond_shared_memory():
     assert kg.bond_dims() == ko.bond_dims()
     assert abs(kg.norm() - ko.norm()) < 1e-9 * ko.norm()
     assert abs(abs(ob.overlap(ko, kg)) / (ko.norm() * kg.norm()) - 1.0) < 1e-9
+
+
+def test_cfg2_full_evaluation_matches_golden(cfg2):
+    """The complete headline workload (400 Trotter steps at chi=100, Nt=201 MPO overlaps, GROUP M=10) against the oracle's
+    golden evaluation (tests/golden/make_golden_cfg2.py): cost 1e-9, gradient 1e-7, identical bond dimensions of every slice."""
+    import os
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, "golden_cfg2_eval.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden_cfg2_eval.npz not generated")
+    import bench
+    oc, st, psi_i, psi_f = cfg2
+    z = np.load(path)
+    basis, c, u = bench.make_problem_host(0)
+    assert np.allclose(c, z["c"]) and np.allclose(u, z["u"])
+    g = oc.OptimalControl(psi_f, psi_i, st, basis, bench.CFG["gamma"])
+    g.setThreadCount(2)
+    grad = np.array(g.getAnalyticGradient(list(c), True))
+    cost = g.getCost(list(c), False)
+    assert abs(cost - float(z["cost"])) / abs(float(z["cost"])) < 1e-9
+    assert np.max(np.abs(grad - z["grad"])) / np.max(np.abs(z["grad"])) < 1e-7
+    fid = np.array(g.getFidelityForAllT(list(c), False))
+    assert np.max(np.abs(fid - z["fidelities"])) < 1e-9
+    assert np.max(np.abs(g.divT - z["divT"])) / np.max(np.abs(z["divT"])) < 1e-7
+    assert np.array_equal(g.psi_t.bond_dims(), z["psi_dims"])
+    assert np.array_equal(g.xi_t.bond_dims(), z["xi_dims"])
