@@ -121,3 +121,27 @@ def test_cfg2_full_evaluation_matches_golden(cfg2):
     assert np.max(np.abs(g.divT - z["divT"])) / np.max(np.abs(z["divT"])) < 1e-7
     assert np.array_equal(g.psi_t.bond_dims(), z["psi_dims"])
     assert np.array_equal(g.xi_t.bond_dims(), z["xi_dims"])
+
+
+@pytest.mark.parametrize("L,Np,chi,cutoff", [(30, 30, 150, 1e-8), (50, 50, 256, 1e-10)])
+def test_cfg4_cfg5_shapes_one_step(L, Np, chi, cutoff):
+    """BASELINE.json configs[3] (L=30, chi=150) and configs[4] (L=50, chi=256, Cutoff 1e-10) at their full shapes: one forward
+    and one backward Trotter step of a random number-conserving MPS (every bond saturated) against the oracle."""
+    import optimalcontrolmps_b200 as oc
+    from oracle import bh_mps as ob
+    from conftest import random_symmetric_mps
+    d = 5
+    psi = random_symmetric_mps(L, d + 1, Np, chi, seed=L)
+    assert max(psi.bond_dims()) == chi
+    so = ob.BHStepper(L, d + 1, 1.0, 1e-2, ob.TruncArgs(cutoff=cutoff, maxm=chi))
+    st = oc.BH_tDMRG(oc.BoseHubbard(L, d), 1.0, 1e-2, oc.Args("Cutoff=", cutoff, "Maxm=", chi))
+    dev = st.to_device(to_host(psi))
+    po = psi.copy()
+    for (a, b, fwd) in [(3.0, 4.0, True), (4.0, 3.5, False)]:
+        so.step(po, a, b, fwd)
+        st.step(dev, a, b, fwd)
+        got = to_oracle(dev.download())
+        assert got.bond_dims() == po.bond_dims()
+        assert abs(abs(ob.overlap(po, got)) - 1.0) < 1e-9
+        assert abs(dev.norm() - 1.0) < 1e-12
+    assert got.check_charges() == 0.0
