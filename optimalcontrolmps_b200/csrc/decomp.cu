@@ -14,10 +14,12 @@
 //      the Gram diagonal (squared norms) is the spectrum the truncation rule sees;
 //   3. after the global truncation, only the kept left vectors are formed, u_j = M z_j^H / |M z_j^H|.
 // One CTA per block.
+#include <cstdio>
 #include "ocmps_internal.h"
 
 __device__ unsigned long long g_jac_dbg[8];
-__device__ double g_jac_flops[2];             // algorithmic flops of the decompositions: [0] block-summed, [1] dense formula   // [0] sum of sweeps, [1] blocks, [2] max sweeps, [3] sweeps of blocks with nv>=64, [4] such blocks
+__device__ double g_jac_flops[2];
+__device__ unsigned long long g_jac_dbg2[8];             // algorithmic flops of the decompositions: [0] block-summed, [1] dense formula   // [0] sum of sweeps, [1] blocks, [2] max sweeps, [3] sweeps of blocks with nv>=64, [4] such blocks
 
 namespace {
 
@@ -180,7 +182,10 @@ __device__ __forceinline__ double half_sum(double v) {
   return v;
 }
 
-template <bool SMEM>
+// SMEM: the block lives in shared memory (else in the global scratch); CACHED: rows are at most 16*JAC_EPL long and a
+// pair's elements stay in registers between the dot product and the rotation.  A block is handled by exactly one
+// instantiation; splitting them keeps the hot loop of the common case small enough for the instruction caches.
+template <bool SMEM, bool CACHED>
 __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a, DecompBuffers b, int smem_elems, double rank_tol) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_rot, s_keff, s_big;
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   const DecompBlock B = w->blk[blockIdx.x];
   const int nv = B.nv, len = B.len, ld = w->ld, mode = w->mode;
   const bool fits = nv * len <= smem_elems && nv <= JAC_NV_SMEM;
-  if (fits != SMEM) return;             // the other instantiation handles this block
+  if (fits != SMEM || (SMEM && (nv <= 16 * JAC_EPL) != CACHED)) return;   // another instantiation handles this block
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = JAC_THREADS / 32;
   const int half = lane >> 4, hl = lane & 15;
   cplx* Ya = b.ywork + B.ws_off;                       // region A: final Z (k x nv, physical vector order)
@@ -280,51 +285,64 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
     const double rb = rsqrt(normx * (normx + aabs));
     const double beta = rb * rb;
     if (tid == 0) { rdr[j] = -phr * normx; rdi[j] = -phi * normx; perm[j] = (short)pv; }   // R_jj; final position j
-    // apply H = I - beta v v^H to the remaining vectors, one half-warp per vector
-    for (int ib = j + 1 + 2 * warp; ib < nv; ib += 2 * nwarps) {
-      const int i = ib + half;
-      const bool act = i < nv;
-      const int phys = act ? (i == bpos ? pj : (int)pcur[i]) : pv;
-      cplx* y = Y + phys * len;
-      double wr = 0.0, wi = 0.0;
-      if (act) {
+    // apply H = I - beta v v^H to the remaining vectors: one half-warp per vector, two vectors in flight per
+    // half-warp (independent dependency chains hide the FP64 / shuffle latencies)
+    for (int ib = j + 1 + 2 * warp; ib < nv; ib += 4 * nwarps) {
+      const int i0 = ib + half, i1 = i0 + 2 * nwarps;
+      const bool act0 = i0 < nv, act1 = i1 < nv;
+      const int phys0 = act0 ? (i0 == bpos ? pj : (int)pcur[i0]) : pv;
+      const int phys1 = act1 ? (i1 == bpos ? pj : (int)pcur[i1]) : pv;
+      cplx* y0 = Y + phys0 * len;
+      cplx* y1 = Y + phys1 * len;
+      double w0r = 0.0, w0i = 0.0, w1r = 0.0, w1i = 0.0;
+      for (int c = j + hl; c < len; c += 16) {
+        cplx vv = x[c];
+        if (c == j) { vv.x = v0r; vv.y = v0i; }
+        if (act0) { const cplx yy = y0[c]; w0r += vv.x * yy.x + vv.y * yy.y; w0i += vv.x * yy.y - vv.y * yy.x; }   // conj(v) * y
+        if (act1) { const cplx yy = y1[c]; w1r += vv.x * yy.x + vv.y * yy.y; w1i += vv.x * yy.y - vv.y * yy.x; }
+      }
+      w0r = half_sum(w0r); w0i = half_sum(w0i); w1r = half_sum(w1r); w1i = half_sum(w1i);
+      double r0 = 0.0, r1 = 0.0;
+      {
+        const double f0r = beta * w0r, f0i = beta * w0i, f1r = beta * w1r, f1i = beta * w1i;
         for (int c = j + hl; c < len; c += 16) {
           cplx vv = x[c];
           if (c == j) { vv.x = v0r; vv.y = v0i; }
-          const cplx yy = y[c];
-          wr += vv.x * yy.x + vv.y * yy.y;      // conj(v) * y
-          wi += vv.x * yy.y - vv.y * yy.x;
+          if (act0) {
+            cplx yy = y0[c];
+            yy.x -= f0r * vv.x - f0i * vv.y;
+            yy.y -= f0r * vv.y + f0i * vv.x;
+            y0[c] = yy;
+            if (c == j) r0 = yy.x * yy.x + yy.y * yy.y;
+          }
+          if (act1) {
+            cplx yy = y1[c];
+            yy.x -= f1r * vv.x - f1i * vv.y;
+            yy.y -= f1r * vv.y + f1i * vv.x;
+            y1[c] = yy;
+            if (c == j) r1 = yy.x * yy.x + yy.y * yy.y;
+          }
         }
       }
-      wr = half_sum(wr); wi = half_sum(wi);
-      double rji2 = 0.0;
-      if (act) {
-        const double fr = beta * wr, fi = beta * wi;
-        for (int c = j + hl; c < len; c += 16) {
-          cplx vv = x[c];
-          if (c == j) { vv.x = v0r; vv.y = v0i; }
-          cplx yy = y[c];
-          yy.x -= fr * vv.x - fi * vv.y;
-          yy.y -= fr * vv.y + fi * vv.x;
-          y[c] = yy;
-          if (c == j) rji2 = yy.x * yy.x + yy.y * yy.y;
-        }
+      // the lane that owns component j (lane 0 of the half-warp) holds |r_ji|^2
+      r0 = __shfl_sync(0xffffffffu, r0, lane & 16);
+      r1 = __shfl_sync(0xffffffffu, r1, lane & 16);
+      double t0n = 0.0, t1n = 0.0;
+      bool redo0 = false, redo1 = false;
+      if (act0) { t0n = ncur[phys0] - r0; redo0 = !(t0n > 1.5e-8 * nrmref[phys0]); }
+      if (act1) { t1n = ncur[phys1] - r1; redo1 = !(t1n > 1.5e-8 * nrmref[phys1]); }
+      if (__any_sync(0xffffffffu, redo0 || redo1)) {     // rare: exact trailing norms
+        double tail0 = 0.0, tail1 = 0.0;
+        if (redo0) for (int c = j + 1 + hl; c < len; c += 16) { const cplx yy = y0[c]; tail0 += yy.x * yy.x + yy.y * yy.y; }
+        if (redo1) for (int c = j + 1 + hl; c < len; c += 16) { const cplx yy = y1[c]; tail1 += yy.x * yy.x + yy.y * yy.y; }
+        tail0 = half_sum(tail0); tail1 = half_sum(tail1);
+        if (redo0) { t0n = tail0; if (hl == 0) nrmref[phys0] = tail0; }
+        if (redo1) { t1n = tail1; if (hl == 0) nrmref[phys1] = tail1; }
       }
-      // the lane that owns component j holds |r_ji|^2: broadcast inside the half-warp
-      rji2 = __shfl_sync(0xffffffffu, rji2, lane & 16);        // component j is owned by lane 0 of the half-warp
-      double tnew = 0.0;
-      bool redo = false;
-      if (act) {
-        tnew = ncur[phys] - rji2;
-        redo = !(tnew > 1.5e-8 * nrmref[phys]);
+      if (hl == 0) {
+        if (act0) { nnext[phys0] = t0n > 0.0 ? t0n : 0.0; pnext[i0] = (short)phys0; }
+        if (act1) { nnext[phys1] = t1n > 0.0 ? t1n : 0.0; pnext[i1] = (short)phys1; }
       }
-      if (__any_sync(0xffffffffu, redo)) {     // rare: exact trailing norm
-        double tail = 0.0;
-        if (act && redo) for (int c = j + 1 + hl; c < len; c += 16) { const cplx yy = y[c]; tail += yy.x * yy.x + yy.y * yy.y; }
-        tail = half_sum(tail);
-        if (act && redo) { tnew = tail; if (hl == 0) nrmref[phys] = tail; }
-      }
-      if (act && hl == 0) { nnext[phys] = tnew > 0.0 ? tnew : 0.0; pnext[i] = (short)phys; }
     }
     __syncthreads();
     { double* t = ncur; ncur = nnext; nnext = t; short* u = pcur; pcur = pnext; pnext = u; }
@@ -353,7 +371,8 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   const int npad = (keff + 1) & ~1;
   const int npairs = npad / 2;
   const double thr = F * DEFLATE_REL;
-  const bool cached = nv <= 16 * JAC_EPL;
+  constexpr bool cached = CACHED;
+  const int epl = (nv + 15) >> 4;                  // elements per lane of a row
   bool converged = false;
   for (int sweep = 0; sweep < JAC_MAX_SWEEPS && !converged; ++sweep) {
     for (int v = warp; v < keff; v += nwarps) {        // exact Gram diagonal at the start of every sweep
@@ -381,24 +400,20 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
         cplx ru[JAC_EPL], rv[JAC_EPL];                 // the pair's elements stay in registers between dot and update
         if (act) {
           if (cached) {
+            // epl = ceil(nv / 16) is uniform: the guards below are branches, so unused slots issue nothing
+            // (the FP64 pipe, 2 cycles per warp instruction and 23 cycles of latency, is what bounds a round)
+            double c0r = 0.0, c0i = 0.0, c1r = 0.0, c1i = 0.0;
 #pragma unroll
             for (int e = 0; e < JAC_EPL; ++e) {
+              if (e >= epl) break;
               const int c = hl + 16 * e;
               ru[e] = make_double2(0.0, 0.0); rv[e] = make_double2(0.0, 0.0);
               if (c < nv) { ru[e] = yp[c]; rv[e] = yq[c]; }
+              const double pr = ru[e].x * rv[e].x + ru[e].y * rv[e].y;      // conj(u) * v
+              const double pi = ru[e].x * rv[e].y - ru[e].y * rv[e].x;
+              if (e & 1) { c1r += pr; c1i += pi; } else { c0r += pr; c0i += pi; }
             }
-            // conj(u) * v with short dependency chains: independent products, pairwise tree
-            double pr[JAC_EPL], pi[JAC_EPL];
-#pragma unroll
-            for (int e = 0; e < JAC_EPL; ++e) {
-              pr[e] = ru[e].x * rv[e].x + ru[e].y * rv[e].y;
-              pi[e] = ru[e].x * rv[e].y - ru[e].y * rv[e].x;
-            }
-#pragma unroll
-            for (int w2 = JAC_EPL / 2; w2 > 0; w2 >>= 1)
-#pragma unroll
-              for (int e = 0; e < w2; ++e) { pr[e] += pr[e + w2]; pi[e] += pi[e + w2]; }
-            cre = pr[0]; cim = pi[0];
+            cre = c0r + c1r; cim = c0i + c1i;
           } else {
             for (int c = hl; c < nv; c += 16) {
               cplx u = yp[c], v = yq[c];
@@ -430,6 +445,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
           if (cached) {
 #pragma unroll
             for (int e = 0; e < JAC_EPL; ++e) {
+              if (e >= epl) break;
               const int c = hl + 16 * e;
               if (c < nv) {
                 const double vx = phr * rv[e].x + phi * rv[e].y, vy = phr * rv[e].y - phi * rv[e].x;
@@ -858,7 +874,7 @@ void profile_read(double* out) {
 }
 
 void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_launch, size_t smem_limit, bool need_global,
-                          double rank_tol, cudaStream_t s) {
+                          bool long_rows, double rank_tol, cudaStream_t s) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof_on) {
     if (g_prof_used == g_prof_events.size()) {
@@ -874,12 +890,14 @@ void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !g_jac_attr_set[dev]) {
-    cudaFuncSetAttribute(jacobi_blocks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(jacobi_blocks_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(jacobi_blocks_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(build_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     g_jac_attr_set[dev] = true;
   }
-  jacobi_blocks_kernel<true><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
-  if (need_global) jacobi_blocks_kernel<false><<<nblk_launch, JAC_THREADS, 0, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
+  jacobi_blocks_kernel<true, true><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
+  if (long_rows) jacobi_blocks_kernel<true, false><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
+  if (need_global) jacobi_blocks_kernel<false, false><<<nblk_launch, JAC_THREADS, 0, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
 }
 
 void launch_truncate(const DecompArgs& a, const DecompBuffers& b, const TruncParams& tp, cudaStream_t s) {

@@ -403,10 +403,11 @@ void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int c
   // numerical-rank tolerance of the pivoted QR: the neglected weight stays >= 6 orders below the cutoff
   double rank_tol = 1e-6 * tp.cutoff;
   rank_tol = std::min(1e-14, std::max(1e-30, rank_tol));
-  launch_jacobi_blocks(a, ws->db, nblk, smem, need_global, rank_tol, s);
+  const bool long_rows = capV > 128;                   // rows of R longer than the register-cached path handles
+  launch_jacobi_blocks(a, ws->db, nblk, smem, need_global, long_rows, rank_tol, s);
   launch_truncate(a, ws->db, tp, s);
   launch_build_factors(a, ws->db, capK, capV, capC, s);
-  g_ocmps_launches += 4 + (need_global ? 1 : 0);
+  g_ocmps_launches += 4 + (need_global ? 1 : 0) + (long_rows ? 1 : 0);
 }
 
 void phases_of(int D, double U, double tstep, double* re, double* im) {
@@ -1343,11 +1344,13 @@ int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* x
   // longest rows first, dealt round-robin to the chains.  Host threads (the reference's work-queue threads,
   // src/OptimalControl.cpp:305-335) each drive a subset of the chains; a thread advances its chains in lock step so
   // that all of its streams stay fed.
+  // Work queue (the reference's mutex-guarded row counter, src/OptimalControl.cpp:305-335): rows sorted by decreasing
+  // length; a chain that has enqueued the last step of its row takes the next row of the queue.  All chains advance one
+  // step per pass of the loop below, so this is longest-processing-time list scheduling of the rows onto the chains.
   std::vector<int> order(rows, rows + nrows);
   std::sort(order.begin(), order.end());
-  struct ChainState { int row = -1; int j = 0; size_t next = 0; };
-  std::vector<std::vector<int>> mine(nchains);
-  for (int i = 0; i < nrows; ++i) mine[i % nchains].push_back(order[i]);
+  struct ChainState { int row = -1; int j = 0; };
+  std::atomic<int> next_row{0};
   std::vector<ChainState> cs(nchains);
   const int hw = (int)std::thread::hardware_concurrency();
   (void)hw;
@@ -1366,8 +1369,9 @@ int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* x
         ChainState& S = cs[c];
         Workspace* ws = wss[c];
         if (S.row < 0) {
-          if (S.next >= mine[c].size()) continue;
-          S.row = mine[c][S.next++];
+          const int qi = next_row.fetch_add(1);
+          if (qi >= nrows) { next_row.store(nrows); continue; }
+          S.row = order[qi];
           if (S.row < 1 || S.row > Nt - 2) { lrc = fail(OCMPS_ERR_INVALID, "hessian row out of range [1, Nt-2]"); break; }
           // psiH = K|psi_row>, its norm, diagonal overlap (src/OptimalControl.cpp:256-264)
           lrc = store_get_async(psi_store, S.row, ws->work, ws->stream);
