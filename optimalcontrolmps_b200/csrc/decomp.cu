@@ -17,9 +17,11 @@
 #include <cstdio>
 #include "ocmps_internal.h"
 
+// development counters: [0] sum of sweeps, [1] blocks, [2] max sweeps, [3] sweeps of blocks with nv >= 64, [4] such blocks,
+// [5] QR clocks, [6] Jacobi clocks, [7] total clocks of those blocks
 __device__ unsigned long long g_jac_dbg[8];
+// algorithmic flops of the decompositions: [0] block-summed, [1] dense formula
 __device__ double g_jac_flops[2];
-__device__ unsigned long long g_jac_dbg2[8];             // algorithmic flops of the decompositions: [0] block-summed, [1] dense formula   // [0] sum of sweeps, [1] blocks, [2] max sweeps, [3] sweeps of blocks with nv>=64, [4] such blocks
 
 namespace {
 
