@@ -48,13 +48,6 @@ __device__ __forceinline__ Geometry geometry(const DecompArgs& a, int chiL, int 
   }
   return g;
 }
-__device__ __forceinline__ int row_charge(const DecompArgs& a, int i) {
-  return (a.kind == DK_ORTH_RIGHT) ? a.qL[i] : a.qL[i / a.D] + i % a.D;
-}
-__device__ __forceinline__ int col_charge(const DecompArgs& a, int j, int chiR) {
-  return (a.kind == DK_ORTH_LEFT) ? a.qR[j] : a.qR[j % chiR] - j / chiR;
-}
-
 // Block table and index lists of one decomposition.  Bond charges are kept sorted ascending by the engine
 // (upload sorts, truncation emits sorted labels), so the members of a charge bin are a handful of contiguous
 // index ranges and every list entry can be placed independently: rank within the bin = (ranges of smaller s)
