@@ -280,64 +280,118 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
     const double rb = rsqrt(normx * (normx + aabs));
     const double beta = rb * rb;
     if (tid == 0) { rdr[j] = -phr * normx; rdi[j] = -phi * normx; perm[j] = (short)pv; }   // R_jj; final position j
-    // apply H = I - beta v v^H to the remaining vectors: one half-warp per vector, two vectors in flight per
-    // half-warp (independent dependency chains hide the FP64 / shuffle latencies)
-    for (int ib = j + 1 + 2 * warp; ib < nv; ib += 4 * nwarps) {
-      const int i0 = ib + half, i1 = i0 + 2 * nwarps;
-      const bool act0 = i0 < nv, act1 = i1 < nv;
-      const int phys0 = act0 ? (i0 == bpos ? pj : (int)pcur[i0]) : pv;
-      const int phys1 = act1 ? (i1 == bpos ? pj : (int)pcur[i1]) : pv;
-      cplx* y0 = Y + phys0 * len;
-      cplx* y1 = Y + phys1 * len;
-      double w0r = 0.0, w0i = 0.0, w1r = 0.0, w1i = 0.0;
-      for (int c = j + hl; c < len; c += 16) {
-        cplx vv = x[c];
-        if (c == j) { vv.x = v0r; vv.y = v0i; }
-        if (act0) { const cplx yy = y0[c]; w0r += vv.x * yy.x + vv.y * yy.y; w0i += vv.x * yy.y - vv.y * yy.x; }   // conj(v) * y
-        if (act1) { const cplx yy = y1[c]; w1r += vv.x * yy.x + vv.y * yy.y; w1i += vv.x * yy.y - vv.y * yy.x; }
+    // apply H = I - beta v v^H to the remaining vectors, one half-warp per vector.  With at most 16*JAC_EPL
+    // components the Householder vector and the target vector live in registers (fully unrolled, uniform guards):
+    // the step is bound by instruction latency, so address arithmetic and loop overhead matter.
+    const int nrem = len - j;                              // components j .. len-1
+    if (CACHED && len <= 16 * JAC_EPL) {
+      const int eplq = (nrem + 15) >> 4;
+      cplx xv[JAC_EPL];
+#pragma unroll
+      for (int e = 0; e < JAC_EPL; ++e) {
+        if (e >= eplq) break;
+        const int c = j + hl + 16 * e;
+        xv[e] = make_double2(0.0, 0.0);
+        if (c < len) xv[e] = x[c];
+        if (c == j) { xv[e].x = v0r; xv[e].y = v0i; }
       }
-      w0r = half_sum(w0r); w0i = half_sum(w0i); w1r = half_sum(w1r); w1i = half_sum(w1i);
-      double r0 = 0.0, r1 = 0.0;
-      {
-        const double f0r = beta * w0r, f0i = beta * w0i, f1r = beta * w1r, f1i = beta * w1i;
+      for (int ib = j + 1 + 2 * warp; ib < nv; ib += 2 * nwarps) {
+        const int i = ib + half;
+        const bool act = i < nv;
+        const int phys = act ? (i == bpos ? pj : (int)pcur[i]) : pv;
+        cplx* y = Y + phys * len;
+        cplx yv[JAC_EPL];
+        double w0r = 0.0, w0i = 0.0, w1r = 0.0, w1i = 0.0;
+#pragma unroll
+        for (int e = 0; e < JAC_EPL; ++e) {
+          if (e >= eplq) break;
+          const int c = j + hl + 16 * e;
+          yv[e] = make_double2(0.0, 0.0);
+          if (act && c < len) yv[e] = y[c];
+          const double pr = xv[e].x * yv[e].x + xv[e].y * yv[e].y;      // conj(v) * y
+          const double pi = xv[e].x * yv[e].y - xv[e].y * yv[e].x;
+          if (e & 1) { w1r += pr; w1i += pi; } else { w0r += pr; w0i += pi; }
+        }
+        double wr = half_sum(w0r + w1r), wi = half_sum(w0i + w1i);
+        const double fr = beta * wr, fi = beta * wi;
+        double rji2 = 0.0;
+#pragma unroll
+        for (int e = 0; e < JAC_EPL; ++e) {
+          if (e >= eplq) break;
+          const int c = j + hl + 16 * e;
+          if (act && c < len) {
+            cplx yy = yv[e];
+            yy.x -= fr * xv[e].x - fi * xv[e].y;
+            yy.y -= fr * xv[e].y + fi * xv[e].x;
+            y[c] = yy;
+            yv[e] = yy;
+            if (e == 0 && hl == 0) rji2 = yy.x * yy.x + yy.y * yy.y;
+          }
+        }
+        rji2 = __shfl_sync(0xffffffffu, rji2, lane & 16);     // component j is owned by lane 0 of the half-warp
+        double tnew = 0.0;
+        bool redo = false;
+        if (act) { tnew = ncur[phys] - rji2; redo = !(tnew > 1.5e-8 * nrmref[phys]); }
+        if (__any_sync(0xffffffffu, redo)) {                   // rare: exact trailing norm
+          double tail = 0.0;
+          if (redo) {
+#pragma unroll
+            for (int e = 0; e < JAC_EPL; ++e) {
+              if (e >= eplq) break;
+              const int c = j + hl + 16 * e;
+              if (c > j && c < len) tail += yv[e].x * yv[e].x + yv[e].y * yv[e].y;
+            }
+          }
+          tail = half_sum(tail);
+          if (redo) { tnew = tail; if (hl == 0) nrmref[phys] = tail; }
+        }
+        if (act && hl == 0) { nnext[phys] = tnew > 0.0 ? tnew : 0.0; pnext[i] = (short)phys; }
+      }
+    } else {
+    for (int ib = j + 1 + 2 * warp; ib < nv; ib += 2 * nwarps) {
+      const int i = ib + half;
+      const bool act = i < nv;
+      const int phys = act ? (i == bpos ? pj : (int)pcur[i]) : pv;
+      cplx* y = Y + phys * len;
+      double wr = 0.0, wi = 0.0;
+      if (act) {
         for (int c = j + hl; c < len; c += 16) {
           cplx vv = x[c];
           if (c == j) { vv.x = v0r; vv.y = v0i; }
-          if (act0) {
-            cplx yy = y0[c];
-            yy.x -= f0r * vv.x - f0i * vv.y;
-            yy.y -= f0r * vv.y + f0i * vv.x;
-            y0[c] = yy;
-            if (c == j) r0 = yy.x * yy.x + yy.y * yy.y;
-          }
-          if (act1) {
-            cplx yy = y1[c];
-            yy.x -= f1r * vv.x - f1i * vv.y;
-            yy.y -= f1r * vv.y + f1i * vv.x;
-            y1[c] = yy;
-            if (c == j) r1 = yy.x * yy.x + yy.y * yy.y;
-          }
+          const cplx yy = y[c];
+          wr += vv.x * yy.x + vv.y * yy.y;      // conj(v) * y
+          wi += vv.x * yy.y - vv.y * yy.x;
         }
       }
-      // the lane that owns component j (lane 0 of the half-warp) holds |r_ji|^2
-      r0 = __shfl_sync(0xffffffffu, r0, lane & 16);
-      r1 = __shfl_sync(0xffffffffu, r1, lane & 16);
-      double t0n = 0.0, t1n = 0.0;
-      bool redo0 = false, redo1 = false;
-      if (act0) { t0n = ncur[phys0] - r0; redo0 = !(t0n > 1.5e-8 * nrmref[phys0]); }
-      if (act1) { t1n = ncur[phys1] - r1; redo1 = !(t1n > 1.5e-8 * nrmref[phys1]); }
-      if (__any_sync(0xffffffffu, redo0 || redo1)) {     // rare: exact trailing norms
-        double tail0 = 0.0, tail1 = 0.0;
-        if (redo0) for (int c = j + 1 + hl; c < len; c += 16) { const cplx yy = y0[c]; tail0 += yy.x * yy.x + yy.y * yy.y; }
-        if (redo1) for (int c = j + 1 + hl; c < len; c += 16) { const cplx yy = y1[c]; tail1 += yy.x * yy.x + yy.y * yy.y; }
-        tail0 = half_sum(tail0); tail1 = half_sum(tail1);
-        if (redo0) { t0n = tail0; if (hl == 0) nrmref[phys0] = tail0; }
-        if (redo1) { t1n = tail1; if (hl == 0) nrmref[phys1] = tail1; }
+      wr = half_sum(wr); wi = half_sum(wi);
+      double rji2 = 0.0;
+      if (act) {
+        const double fr = beta * wr, fi = beta * wi;
+        for (int c = j + hl; c < len; c += 16) {
+          cplx vv = x[c];
+          if (c == j) { vv.x = v0r; vv.y = v0i; }
+          cplx yy = y[c];
+          yy.x -= fr * vv.x - fi * vv.y;
+          yy.y -= fr * vv.y + fi * vv.x;
+          y[c] = yy;
+          if (c == j) rji2 = yy.x * yy.x + yy.y * yy.y;
+        }
       }
-      if (hl == 0) {
-        if (act0) { nnext[phys0] = t0n > 0.0 ? t0n : 0.0; pnext[i0] = (short)phys0; }
-        if (act1) { nnext[phys1] = t1n > 0.0 ? t1n : 0.0; pnext[i1] = (short)phys1; }
+      rji2 = __shfl_sync(0xffffffffu, rji2, lane & 16);        // component j is owned by lane 0 of the half-warp
+      double tnew = 0.0;
+      bool redo = false;
+      if (act) {
+        tnew = ncur[phys] - rji2;
+        redo = !(tnew > 1.5e-8 * nrmref[phys]);
       }
+      if (__any_sync(0xffffffffu, redo)) {     // rare: exact trailing norm
+        double tail = 0.0;
+        if (act && redo) for (int c = j + 1 + hl; c < len; c += 16) { const cplx yy = y[c]; tail += yy.x * yy.x + yy.y * yy.y; }
+        tail = half_sum(tail);
+        if (act && redo) { tnew = tail; if (hl == 0) nrmref[phys] = tail; }
+      }
+      if (act && hl == 0) { nnext[phys] = tnew > 0.0 ? tnew : 0.0; pnext[i] = (short)phys; }
+    }
     }
     __syncthreads();
     { double* t = ncur; ncur = nnext; nnext = t; short* u = pcur; pcur = pnext; pnext = u; }
