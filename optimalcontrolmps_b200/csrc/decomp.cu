@@ -111,7 +111,12 @@ __global__ void __launch_bounds__(SETUP_THREADS) decomp_setup_kernel(DecompArgs 
           B.q = c; B.nv = cnt_v[c]; B.len = cnt_c[c];
           B.vec_off = ov; B.comp_off = oc; B.ws_off = ows; B.p_off = ov; B.pad = 0;
           w->blk[nb] = B;
-          ov += cnt_v[c]; oc += cnt_c[c]; ows += cnt_v[c] * cnt_c[c];
+          {   // workspace of the block: nv*len for the vectors, or (rows of R) x (row stride padded to 16) if larger
+            const int nvq = cnt_v[c], lenq = cnt_c[c];
+            const int padded = (nvq < lenq ? nvq : lenq) * (((nvq + 15) >> 4) << 4);
+            ows += nvq * lenq > padded ? nvq * lenq : padded;
+          }
+          ov += cnt_v[c]; oc += cnt_c[c];
           ++nb;
         } else {
           atomicOr(b.status, OCMPS_ST_TOOMANYBLK);
@@ -193,7 +198,10 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   const DecompBlock B = w->blk[blockIdx.x];
   const int nv = B.nv, len = B.len, ld = w->ld, mode = w->mode;
   const bool fits = nv * len <= smem_elems && nv <= JAC_NV_SMEM;
-  if (fits != SMEM || (SMEM && (nv <= 16 * JAC_EPL) != CACHED)) return;   // another instantiation handles this block
+  // register-cached variant: rows of R at most 16*JAC_EPL long, stored with a zero-padded stride of 16*ceil(nv/16)
+  const int ldpad = ((nv + 15) >> 4) << 4;
+  const bool can_cache = nv <= 16 * JAC_EPL && (nv < len ? nv : len) * ldpad <= smem_elems;
+  if (fits != SMEM || (SMEM && can_cache != CACHED)) return;   // another instantiation handles this block
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = JAC_THREADS / 32;
   const int half = lane >> 4, hl = lane & 15;
   cplx* Ya = b.ywork + B.ws_off;                       // region A: final Z (k x nv, physical vector order)
@@ -401,17 +409,18 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   if (tid == 0) s_keff = keff;
 
   // ---- phase 2: R (keff x nv, position order) -> row-major scratch -> back as the Jacobi working set ----
-  for (int e = tid; e < keff * nv; e += JAC_THREADS) {
-    const int c = e / nv, i = e % nv;
+  const int ldz = CACHED ? ldpad : nv;            // row stride of the Jacobi working set (padding is zero)
+  for (int e = tid; e < keff * ldz; e += JAC_THREADS) {
+    const int c = e / ldz, i = e % ldz;
     cplx v = make_double2(0.0, 0.0);
     if (i == c) v = make_double2(rdr[c], rdi[c]);
-    else if (i > c) v = Y[(int)perm[i] * len + c];
+    else if (i > c && i < nv) v = Y[(int)perm[i] * len + c];
     Yb[e] = v;
   }
   __syncthreads();
   cplx* Z = SMEM ? Y : Yb;
   if (SMEM) {
-    for (int e = tid; e < keff * nv; e += JAC_THREADS) Z[e] = Yb[e];
+    for (int e = tid; e < keff * ldz; e += JAC_THREADS) Z[e] = Yb[e];
     __syncthreads();
   }
 
@@ -425,7 +434,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   bool converged = false;
   for (int sweep = 0; sweep < JAC_MAX_SWEEPS && !converged; ++sweep) {
     for (int v = warp; v < keff; v += nwarps) {        // exact Gram diagonal at the start of every sweep
-      const cplx* y = Z + v * nv;
+      const cplx* y = Z + v * ldz;
       double s = 0.0;
       for (int c = lane; c < nv; c += 32) { cplx u = y[c]; s += u.x * u.x + u.y * u.y; }
       s = warp_sum(s);
@@ -443,8 +452,8 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
         if (k == 0) q = npad - 1;
         const bool act = (k < npairs) && p < keff && q < keff;
         if (p > q) { int tmp = p; p = q; q = tmp; }
-        cplx* yp = Z + (act ? p : 0) * nv;
-        cplx* yq = Z + (act ? q : 0) * nv;
+        cplx* yp = Z + (act ? p : 0) * ldz;
+        cplx* yq = Z + (act ? q : 0) * ldz;
         double cre = 0.0, cim = 0.0;
         cplx ru[JAC_EPL], rv[JAC_EPL];                 // the pair's elements stay in registers between dot and update
         if (act) {
@@ -456,8 +465,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
             for (int e = 0; e < JAC_EPL; ++e) {
               if (e >= epl) break;
               const int c = hl + 16 * e;
-              ru[e] = make_double2(0.0, 0.0); rv[e] = make_double2(0.0, 0.0);
-              if (c < nv) { ru[e] = yp[c]; rv[e] = yq[c]; }
+              ru[e] = yp[c]; rv[e] = yq[c];                       // the padding of a row is zero
               const double pr = ru[e].x * rv[e].x + ru[e].y * rv[e].y;      // conj(u) * v
               const double pi = ru[e].x * rv[e].y - ru[e].y * rv[e].x;
               if (e & 1) { c1r += pr; c1i += pi; } else { c0r += pr; c0i += pi; }
@@ -496,11 +504,9 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
             for (int e = 0; e < JAC_EPL; ++e) {
               if (e >= epl) break;
               const int c = hl + 16 * e;
-              if (c < nv) {
-                const double vx = phr * rv[e].x + phi * rv[e].y, vy = phr * rv[e].y - phi * rv[e].x;
-                yp[c] = make_double2(cs * ru[e].x - sn * vx, cs * ru[e].y - sn * vy);
-                yq[c] = make_double2(sn * ru[e].x + cs * vx, sn * ru[e].y + cs * vy);
-              }
+              const double vx = phr * rv[e].x + phi * rv[e].y, vy = phr * rv[e].y - phi * rv[e].x;
+              yp[c] = make_double2(cs * ru[e].x - sn * vx, cs * ru[e].y - sn * vy);
+              yq[c] = make_double2(sn * ru[e].x + cs * vx, sn * ru[e].y + cs * vy);
             }
           } else {
             for (int c = hl; c < nv; c += 16) {
@@ -549,7 +555,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   }
   for (int v = warp; v < nv; v += nwarps) {
     if (v < keff) {
-      const cplx* y = Z + v * nv;
+      const cplx* y = Z + v * ldz;
       double s = 0.0;
       for (int c = lane; c < nv; c += 32) { cplx u = y[c]; s += u.x * u.x + u.y * u.y; }
       s = warp_sum(s);

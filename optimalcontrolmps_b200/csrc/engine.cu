@@ -208,8 +208,10 @@ int alloc_ws(ocmps_ctx* ctx, int L, int D, int cap, bool with_work, Workspace** 
   CK(cudaMalloc(&w->db.vecq, sizeof(int) * NV_MAX));
   CK(cudaMalloc(&w->db.P, sizeof(double) * NV_MAX));
   CK(cudaMalloc(&w->db.pos, sizeof(int) * 3 * NV_MAX));
-  CK(cudaMalloc(&w->db.ywork, sizeof(cplx) * 2 * nD * cap));
-  w->db.ywork_half = (long long)(nD * cap);
+  // per block max(nv*len, rows*pad16(nv)) elements: sum_q <= cap*(D*cap) + cap*16*OCMPS_MAX_BLK
+  const size_t ywhalf = nD * cap + (size_t)cap * 16 * OCMPS_MAX_BLK;
+  CK(cudaMalloc(&w->db.ywork, sizeof(cplx) * 2 * ywhalf));
+  w->db.ywork_half = (long long)ywhalf;
   CK(cudaMalloc(&w->db.scratch_d, sizeof(double) * 8 * NV_MAX));
   CK(cudaMalloc(&w->db.descs, sizeof(GemmDesc) * 4));
   CK(cudaMalloc(&w->db.partial, sizeof(double) * 64));
@@ -394,6 +396,8 @@ void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int c
   launch_decomp_setup(a, ws->db, s);
   // shared memory: the largest block has at most capV vectors of at most capC components
   size_t need = (size_t)capV * capC * sizeof(cplx);
+  // the Jacobi working set stores its rows (<= min(capV, capC) of them) with a stride padded to a multiple of 16
+  need = std::max(need, (size_t)std::min(capV, capC) * (size_t)(((capV + 15) / 16) * 16) * sizeof(cplx));
   size_t smem = std::min(need, JAC_SMEM_LIMIT);
   if (smem < 1024) smem = 1024;
   // blocks are labelled by a charge in [0, qmax + D): launch no more CTAs than that (surplus CTAs would still have to
