@@ -77,9 +77,19 @@ __global__ void __launch_bounds__(256) zgemm_kernel(const GemmDesc* __restrict__
   };
   load_tiles(0);
   for (int k0 = 0; k0 < d.K; k0 += BK) {
+    // MPS tensors are block sparse in the boson number and stored dense with exact zeros: a staged tile of A or of B
+    // that is entirely zero contributes nothing, and most (tile, k-chunk) combinations are of that kind
+    bool nzA = false, nzB = false;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      nzA |= (ra[u].x != 0.0) | (ra[u].y != 0.0);
+      nzB |= (rb[u].x != 0.0) | (rb[u].y != 0.0);
+    }
     store_tiles();
-    __syncthreads();
+    const int anyA = __syncthreads_or(nzA ? 1 : 0);      // (the barrier also publishes the staged tiles)
+    const int anyB = __syncthreads_or(nzB ? 1 : 0);
     if (k0 + BK < d.K) load_tiles(k0 + BK);
+    if (anyA && anyB) {
 #pragma unroll
     for (int k4 = 0; k4 < BK; k4 += 4) {
       const double ar = As_re[warp * 8 + g][k4 + t];
@@ -94,6 +104,7 @@ __global__ void __launch_bounds__(256) zgemm_kernel(const GemmDesc* __restrict__
         dmma(ci[nt][0], ci[nt][1], ar, bi);
         dmma(ci[nt][0], ci[nt][1], ai, br);
       }
+    }
     }
     __syncthreads();
   }
