@@ -576,142 +576,160 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
 // global truncation (ITensor truncate()) + new bond bookkeeping + follow-up descriptor
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) truncate_kernel(DecompArgs a, DecompBuffers b, TruncParams tp) {
-  __shared__ double sP[NV_MAX];
-  __shared__ double sSorted[NV_MAX];      // descending; later overwritten by its suffix sums
-  __shared__ short sQ[NV_MAX];
+  // Only the non-zero weights take part (rows past a block's numerical rank report 0 and can never be kept); they are
+  // compacted first, so the two O(n^2 / threads) ranking loops run over the candidates only.
+  __shared__ double cP[NV_MAX];           // candidate weights, compact
+  __shared__ double sSorted[NV_MAX];      // descending; then overwritten by its suffix sums
+  __shared__ short cQ[NV_MAX], cI[NV_MAX];
   __shared__ unsigned char sKeep[NV_MAX];
-  __shared__ short sPos[NV_MAX];
   __shared__ int sBlkOff[OCMPS_MAX_BLK + 1];
   __shared__ double sWarp[32];
-  __shared__ double s_docut;
+  __shared__ int sWarpCnt[33];
+  __shared__ double s_docut, s_kept;
   __shared__ int s_total, s_nfinal;
-  __shared__ double s_kept;
   DecompWork* w = b.dw;
   const int nv = w->nvtot;
   const int nblocks = w->nblocks;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < nv; i += blockDim.x) { sP[i] = b.P[i]; sQ[i] = (short)b.vecq[i]; }
   for (int i = tid; i < nblocks; i += blockDim.x) sBlkOff[i] = w->blk[i].p_off;
-  if (tid == 0) { s_total = 0; s_nfinal = 0; }
+  if (tid == 0) { s_total = 0; s_nfinal = 0; s_docut = 0.0; }
+  // ---- compaction (order preserving): thread t owns entries 2t, 2t+1 ----
+  const int i0 = 2 * tid, i1 = i0 + 1;
+  const double p0 = i0 < nv ? b.P[i0] : 0.0, p1 = i1 < nv ? b.P[i1] : 0.0;
+  const int f0 = p0 > 0.0, f1 = p1 > 0.0;
+  int incl = f0 + f1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+  if (lane == 31) sWarpCnt[warp + 1] = incl;
+  if (tid == 0) sWarpCnt[0] = 0;
   __syncthreads();
-  for (int i = tid; i < nv; i += blockDim.x) {
-    const double pi = sP[i];
-    int rank = 0;
-    for (int j = 0; j < nv; ++j) {
-      const double pj = sP[j];
-      rank += (pj > pi) || (pj == pi && j < i);
-    }
-    sSorted[rank] = pi;
+  if (warp == 0) {
+    int v = sWarpCnt[lane + 1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int up = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += up; }
+    sWarpCnt[lane + 1] = v;
   }
   __syncthreads();
-  // Suffix sums Suf[n] = sum_{i >= n} sorted[i] (what ITensor's loop accumulates in `truncerr` while it walks down
-  // from the small end), by a block-wide scan: thread t owns the two entries 2t, 2t+1 counted from the END.
-  const int origm = nv;
-  const int e0 = origm - 1 - 2 * tid, e1 = e0 - 1;         // e0 > e1
+  const int nnz = sWarpCnt[32];
+  {
+    int k = sWarpCnt[warp] + incl - f0 - f1;
+    if (f0) { cP[k] = p0; cQ[k] = (short)b.vecq[i0]; cI[k] = (short)i0; ++k; }
+    if (f1) { cP[k] = p1; cQ[k] = (short)b.vecq[i1]; cI[k] = (short)i1; }
+  }
+  __syncthreads();
+  // ---- descending rank of every candidate ----
+  for (int k = tid; k < nnz; k += blockDim.x) {
+    const double pk = cP[k];
+    int rank = 0;
+    for (int j = 0; j < nnz; ++j) {
+      const double pj = cP[j];
+      rank += (pj > pk) || (pj == pk && j < k);
+    }
+    sSorted[rank] = pk;
+  }
+  __syncthreads();
+  // ---- suffix sums Suf[n] = sum_{i >= n} sorted[i] (ITensor accumulates them in `truncerr` walking up from the small
+  // end); block-wide scan, thread t owns the two entries 2t, 2t+1 counted from the END of the candidate list ----
+  const int origm = nv;                                    // ITensor's count includes the zero weights
+  const int e0 = nnz - 1 - 2 * tid, e1 = e0 - 1;           // e0 > e1
   const double v0 = e0 >= 0 ? sSorted[e0] : 0.0, v1 = e1 >= 0 ? sSorted[e1] : 0.0;
   {
-    double run = v0 + v1;                                   // inclusive scan over threads (towards smaller indices)
+    double run = v0 + v1;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double up = __shfl_up_sync(0xffffffffu, run, o);
-      if (lane >= o) run += up;
-    }
+    for (int o = 1; o < 32; o <<= 1) { const double up = __shfl_up_sync(0xffffffffu, run, o); if (lane >= o) run += up; }
     if (lane == 31) sWarp[warp] = run;
     __syncthreads();
     if (warp == 0) {
       double ws = sWarp[lane];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const double up = __shfl_up_sync(0xffffffffu, ws, o);
-        if (lane >= o) ws += up;
-      }
+      for (int o = 1; o < 32; o <<= 1) { const double up = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += up; }
       sWarp[lane] = ws;
     }
     __syncthreads();
     const double base = warp > 0 ? sWarp[warp - 1] : 0.0;
-    const double incl = base + run;                         // sum over entries >= e1
-    if (e0 >= 0) sSorted[e0] = incl - v1;                   // Suf[e0]
-    if (e1 >= 0) sSorted[e1] = incl;                        // Suf[e1]
+    const double inc = base + run;
+    if (e0 >= 0) sSorted[e0] = inc - v1;                    // Suf[e0]
+    if (e1 >= 0) sSorted[e1] = inc;                         // Suf[e1]
   }
   __syncthreads();
   {
-    // final n = largest n <= min(maxm, origm) - 1 with (n < minm or Suf[n] >= cutoff * scale)
-    const double scale = tp.rel_cutoff ? (sSorted[0] == 0.0 ? 1.0 : sSorted[0]) : 1.0;
+    // final n = largest n <= min(maxm, origm) - 1 with (n < minm or Suf[n] >= cutoff * scale); Suf[n] = 0 for n >= nnz
+    const double total_w = nnz > 0 ? sSorted[0] : 0.0;
+    const double scale = tp.rel_cutoff ? (total_w == 0.0 ? 1.0 : total_w) : 1.0;
     const double cut = tp.cutoff * scale;
     const int nmax = (tp.maxm < origm ? tp.maxm : origm) - 1;
     int best = 0;
-    for (int n = tid; n <= nmax; n += blockDim.x)
-      if (n < tp.minm || sSorted[n] >= cut) best = n > best ? n : best;
+    if (cut <= 0.0) {
+      best = nmax > 0 ? nmax : 0;
+    } else {
+      const int lim = nmax < nnz - 1 ? nmax : nnz - 1;
+      for (int n = tid; n <= lim; n += blockDim.x)
+        if (n < tp.minm || sSorted[n] >= cut) best = n > best ? n : best;
+      if (tp.minm - 1 > best && tp.minm - 1 <= nmax) best = tp.minm - 1;
+    }
     if (best > 0) atomicMax(&s_nfinal, best);
   }
   __syncthreads();
   {
-    // docut = midpoint of the two sorted values that straddle the cut (+ the degeneracy bump)
+    // docut = midpoint of the two sorted values that straddle the cut (+ the degeneracy bump); zeros beyond nnz
     const int m = s_nfinal + 1;
-    if (origm == 1) {
-      if (e0 == 0) s_docut = v0 / 2.0;
-    } else if (m < origm) {
-      if (e0 == m) sWarp[0] = v0;
-      if (e1 == m) sWarp[0] = v1;
-      if (e0 == m - 1) sWarp[1] = v0;
-      if (e1 == m - 1) sWarp[1] = v1;
-    } else if (tid == 0) {
-      s_docut = 0.0;
-    }
+    if (tid == 0) { sWarp[0] = 0.0; sWarp[1] = 0.0; }
     __syncthreads();
-    if (tid == 0 && origm > 1 && m < origm) {
-      const double pm = sWarp[0], pm1 = sWarp[1];
-      double docut = (pm + pm1) / 2.0;
-      if (fabs(pm - pm1) < 1e-3 * pm1) docut += 1e-3 * pm1;
+    if (e0 == m) sWarp[0] = v0;
+    if (e1 == m) sWarp[0] = v1;
+    if (e0 == m - 1) sWarp[1] = v0;
+    if (e1 == m - 1) sWarp[1] = v1;
+    __syncthreads();
+    if (tid == 0) {
+      double docut = 0.0;
+      if (origm == 1) {
+        docut = sWarp[1] / 2.0;                             // m - 1 = 0: the only weight
+      } else if (origm > 1 && m < origm) {
+        const double pm = sWarp[0], pm1 = sWarp[1];
+        docut = (pm + pm1) / 2.0;
+        if (fabs(pm - pm1) < 1e-3 * pm1) docut += 1e-3 * pm1;
+      }
       s_docut = docut;
     }
-    if (tid == 0 && origm == 0) s_docut = 0.0;
     __syncthreads();
   }
   const double docut = s_docut;
-  for (int i = tid; i < nv; i += blockDim.x) {
-    const unsigned char k = sP[i] > docut;
-    sKeep[i] = k;
-    if (k) atomicAdd(&s_total, 1);
+  for (int k = tid; k < nnz; k += blockDim.x) {
+    const unsigned char kp = cP[k] > docut;
+    sKeep[k] = kp;
+    if (kp) atomicAdd(&s_total, 1);
   }
   __syncthreads();
-  if (s_total == 0 && nv > 0) {        // zero tensor: keep one arbitrary state
-    if (tid == 0) { sKeep[0] = 1; s_total = 1; }
-    __syncthreads();
-  }
   const int total = s_total;
   int* inv_blk = b.pos + NV_MAX;       // per new index: block id, vector-in-block
   int* inv_v = b.pos + 2 * NV_MAX;
-  for (int i = tid; i < nv; i += blockDim.x) {
-    int pos = -1;
-    if (sKeep[i]) {
-      pos = 0;
-      const int qi = sQ[i];
-      const double pi = sP[i];
-      for (int j = 0; j < nv; ++j) {
-        if (!sKeep[j]) continue;
-        const int qj = sQ[j];
-        const double pj = sP[j];
-        pos += (qj < qi) || (qj == qi && (pj > pi || (pj == pi && j < i)));
-      }
-      if (pos < tp.cap) {
-        a.qNew[pos] = qi;
-        int bi = 0;                      // block of vector i: scan the (short) block table
-        while (bi + 1 < nblocks && sBlkOff[bi + 1] <= i) ++bi;
-        inv_blk[pos] = bi;
-        inv_v[pos] = i - sBlkOff[bi];
-      }
+  double part = 0.0;
+  for (int k = tid; k < nnz; k += blockDim.x) {
+    if (!sKeep[k]) continue;
+    const int qk = cQ[k];
+    const double pk = cP[k];
+    int pos = 0;
+    for (int j = 0; j < nnz; ++j) {
+      if (!sKeep[j]) continue;
+      const int qj = cQ[j];
+      const double pj = cP[j];
+      pos += (qj < qk) || (qj == qk && (pj > pk || (pj == pk && j < k)));
     }
-    b.pos[i] = pos;
-    sPos[i] = (short)pos;
+    if (pos < tp.cap) {
+      const int i = cI[k];
+      a.qNew[pos] = qk;
+      int bi = 0;                      // block of vector i: scan the (short) block table
+      while (bi + 1 < nblocks && sBlkOff[bi + 1] <= i) ++bi;
+      inv_blk[pos] = bi;
+      inv_v[pos] = i - sBlkOff[bi];
+      part += pk;
+    }
   }
-  __syncthreads();
   {
-    // sum of the kept weights: per-thread partial sums over a fixed index pattern, fixed-order tree
-    double part = 0.0;
-    for (int i = tid; i < nv; i += blockDim.x) if (sKeep[i] && sPos[i] < tp.cap) part += sP[i];
+    // sum of the kept weights: fixed index pattern per thread, fixed-order tree
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    __syncthreads();
     if (lane == 0) sWarp[warp] = part;
     __syncthreads();
     if (tid == 0) {
@@ -723,6 +741,12 @@ __global__ void __launch_bounds__(1024) truncate_kernel(DecompArgs a, DecompBuff
   }
   if (tid == 0) {
     int k = total;
+    if (k == 0 && nv > 0) {            // zero tensor: keep one arbitrary state (the first vector of the first block)
+      k = 1;
+      a.qNew[0] = b.vecq[0];
+      inv_blk[0] = 0;
+      inv_v[0] = 0;
+    }
     if (k > tp.cap) { atomicOr(b.status, OCMPS_ST_CAPACITY); k = tp.cap; }
     w->newdim = k;
     *a.dimNew = k;
