@@ -29,6 +29,7 @@ constexpr int JAC_THREADS = 512;
 constexpr int JAC_EPL = 8;                // elements per lane cached in registers (rows up to 16*8 = 128 long)
 constexpr int JAC_NV_SMEM = 512;          // cached norms in shared memory for blocks with at most this many vectors
 constexpr int JAC_MAX_SWEEPS = 60;
+constexpr int JAC_BLOCKED_ROWS = 64;      // 4 rows per warp, JAC_THREADS / 32 warps
 constexpr double JAC_TOL2 = 1e-28;        // rotate while |<p|q>|^2 > tol^2 <p|p><q|q>, tol = 1e-14
 constexpr double DEFLATE_REL = 1e-30;     // vectors below this fraction of the block's weight are numerically zero
 constexpr int NV_MAX = 2048;              // max number of vectors in one decomposition
@@ -180,6 +181,144 @@ __device__ __forceinline__ double half_sum(double v) {
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// One plane rotation of the rows a, b (16*EPL long, one half-warp, EPL elements per lane) that annihilates <a|b>.
+// na, nb are the cached squared norms.  All 32 lanes must call (shuffles); `act` is uniform per half-warp.
+template <int EPL>
+__device__ __forceinline__ void jac_rotate(cplx (&ra)[EPL], cplx (&rb)[EPL], double& na, double& nb, bool act, double thr,
+                                           int hl, int* s_rot, int* s_big) {
+  double c0r = 0.0, c0i = 0.0, c1r = 0.0, c1i = 0.0;
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const double pr = ra[e].x * rb[e].x + ra[e].y * rb[e].y;      // conj(a) * b
+    const double pi = ra[e].x * rb[e].y - ra[e].y * rb[e].x;
+    if (e & 1) { c1r += pr; c1i += pi; } else { c0r += pr; c0i += pi; }
+  }
+  const double cre = half_sum(c0r + c1r), cim = half_sum(c0i + c1i);
+  if (!act) return;
+  const double aa = na, bb = nb;
+  const double c2 = cre * cre + cim * cim;
+  if (aa <= thr || bb <= thr) {
+    if (aa <= thr && aa > 0.0) {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) ra[e] = make_double2(0.0, 0.0);
+      na = 0.0;
+    }
+    if (bb <= thr && bb > 0.0) {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) rb[e] = make_double2(0.0, 0.0);
+      nb = 0.0;
+    }
+  } else if (c2 > JAC_TOL2 * aa * bb) {
+    // tan 2theta = |c| / d with d = (b - a)/2.  With h = sqrt(d^2 + |c|^2), s = |d| + h and w = 1/sqrt(2 h s):
+    // cos = s w, sigma = sin e^{i phi} = +-w c, tan(theta) |c| = |c|^2 / s = |c|^2 w^2 2h  (two rsqrt, no division)
+    const double dd = 0.5 * (bb - aa);
+    const double xh = dd * dd + c2;
+    const double ih = rsqrt(xh);
+    const double h = xh * ih;
+    const double sdh = fabs(dd) + h;
+    const double w = rsqrt(2.0 * h * sdh);
+    const double cs = sdh * w;
+    const double sgw = dd >= 0.0 ? w : -w;
+    const double sr = sgw * cre, si = sgw * cim;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const cplx u = ra[e], v = rb[e];
+      ra[e] = make_double2(cs * u.x - (sr * v.x + si * v.y), cs * u.y - (sr * v.y - si * v.x));   // cs a - conj(sigma) b
+      rb[e] = make_double2(cs * v.x + (sr * u.x - si * u.y), cs * v.y + (sr * u.y + si * u.x));   // sigma a + cs b
+    }
+    const double trr = c2 * (sgw * w) * (2.0 * h);
+    const double a1 = aa - trr, b1 = bb + trr;
+    na = a1 > 0.0 ? a1 : 0.0;
+    nb = b1 > 0.0 ? b1 : 0.0;
+    if (hl == 0) {
+      *s_rot = 1;
+      if (c2 > 1e-16 * aa * bb) *s_big = 1;                // an off-diagonal above 1e-8 (relative) was seen
+    }
+  }
+}
+
+// One sweep over all pairs of the keff <= 64 rows of Z (row stride ldz = 16*EPL, zero padded), rows held in registers.
+//
+// A round of the plain scheme moves every row through the 128 B/clk shared-memory crossbar twice and ends in a CTA
+// barrier, which together cost more than the dot -> angle -> rotation latency chain itself.  Here the rows are grouped
+// in blocks of two and a WARP owns a pair of blocks (one row of each per half-warp): the four cross pairs are done in
+// two rounds with a register shuffle in between, and the block-level round-robin is mapped onto the warps such that
+// every warp keeps one of its two blocks from one block round to the next (warp s plays block pair s in even block
+// rounds and s-1 in odd ones).  Per rotation round that is half a row stored and half a row loaded per half-warp
+// instead of two and two, and one CTA barrier per two rounds.  The pairs inside a block are done first.
+template <int EPL>
+__device__ __forceinline__ void jacobi_sweep_blocked(cplx* __restrict__ Z, int keff, double* __restrict__ nrm, double thr, int* s_rot, int* s_big) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = lane >> 4, hl = lane & 15;
+  constexpr int ldz = 16 * EPL;
+  const int nb = (keff + 1) >> 1;            // blocks of two rows
+  const int nbp = (nb + 1) & ~1;             // padded to an even count
+  const int nslots = nbp >> 1, mm = nbp - 1;
+  cplx ra[EPL], rb[EPL];
+  double na = 0.0, nbn = 0.0;
+  auto load_row = [&](cplx (&r)[EPL], double& n, int row) {
+    const cplx* z = Z + (row >= 0 ? row : 0) * ldz + hl;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) r[e] = row >= 0 ? z[16 * e] : make_double2(0.0, 0.0);
+    n = row >= 0 ? nrm[row] : 0.0;
+  };
+  auto store_row = [&](const cplx (&r)[EPL], double n, int row) {
+    if (row < 0) return;
+    cplx* z = Z + row * ldz + hl;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) z[16 * e] = r[e];
+    if (hl == 0) nrm[row] = n;
+  };
+  {   // pairs inside the blocks: half-warp i takes block i
+    const int i = 2 * warp + half;
+    const int x = 2 * i < keff ? 2 * i : -1, y = 2 * i + 1 < keff ? 2 * i + 1 : -1;
+    load_row(ra, na, x);
+    load_row(rb, nbn, y);
+    jac_rotate<EPL>(ra, rb, na, nbn, x >= 0 && y >= 0, thr, hl, s_rot, s_big);
+    store_row(ra, na, x);
+    store_row(rb, nbn, y);
+  }
+  __syncthreads();
+  auto blocks_of = [&](int R, int& P, int& Q) {
+    P = -1; Q = -1;
+    if (warp >= nslots) return;
+    const int k = (R & 1) ? (warp == 0 ? nslots - 1 : warp - 1) : warp;
+    int p = R + k; if (p >= mm) p -= mm;
+    int q = R - k; if (q < 0) q += mm;
+    if (k == 0) q = nbp - 1;
+    P = p < nb ? p : -1;
+    Q = q < nb ? q : -1;
+  };
+  int hbA = -1, hbB = -1;          // blocks in the A / B registers of this warp
+  int rowA = -1, rowB = -1;        // rows in the A / B registers of this half-warp
+  int P, Q;
+  blocks_of(0, P, Q);
+  for (int R = 0; R < nbp - 1; ++R) {
+    if (P != hbA) { rowA = (P >= 0 && 2 * P + half < keff) ? 2 * P + half : -1; load_row(ra, na, rowA); }
+    if (Q != hbB) { rowB = (Q >= 0 && 2 * Q + half < keff) ? 2 * Q + half : -1; load_row(rb, nbn, rowB); }
+    hbA = P; hbB = Q;
+    jac_rotate<EPL>(ra, rb, na, nbn, rowA >= 0 && rowB >= 0, thr, hl, s_rot, s_big);
+    // the two halves swap their B rows: (a0,b0)(a1,b1) -> (a0,b1)(a1,b0)
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      rb[e].x = __shfl_xor_sync(0xffffffffu, rb[e].x, 16);
+      rb[e].y = __shfl_xor_sync(0xffffffffu, rb[e].y, 16);
+    }
+    nbn = __shfl_xor_sync(0xffffffffu, nbn, 16);
+    rowB = __shfl_xor_sync(0xffffffffu, rowB, 16);
+    jac_rotate<EPL>(ra, rb, na, nbn, rowA >= 0 && rowB >= 0, thr, hl, s_rot, s_big);
+    // blocks of the next block round, named such that the block that stays keeps its registers
+    int NP = -1, NQ = -1;
+    if (R + 1 < nbp - 1) {
+      blocks_of(R + 1, NP, NQ);
+      if ((NP >= 0 && NP == hbB) || (NQ >= 0 && NQ == hbA)) { const int t = NP; NP = NQ; NQ = t; }
+    }
+    if (hbA != NP) store_row(ra, na, rowA);
+    if (hbB != NQ) store_row(rb, nbn, rowB);
+    P = NP; Q = NQ;
+    __syncthreads();
+  }
 }
 
 // SMEM: the block lives in shared memory (else in the global scratch); CACHED: rows are at most 16*JAC_EPL long and a
@@ -418,6 +557,32 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
     Yb[e] = v;
   }
   __syncthreads();
+  {
+    // hand-over: blocks whose R has at most JAC_BLOCKED_ROWS rows are finished by jacobi_rot_kernel (register-resident
+    // rows; a kernel of its own so that its register allocation is not shared with the QR phase)
+    double* hF = b.scratch_d + 7 * NV_MAX;
+    int* hK = reinterpret_cast<int*>(b.scratch_d + 7 * NV_MAX + OCMPS_MAX_BLK);
+    const bool handover = CACHED && keff <= JAC_BLOCKED_ROWS;
+    if (tid == 0) { hF[blockIdx.x] = F; hK[blockIdx.x] = handover ? keff : -1; }
+    if (handover) {
+      short* gperm = reinterpret_cast<short*>(b.scratch_d + 4 * NV_MAX) + B.p_off;
+      for (int i = tid; i < nv; i += JAC_THREADS) gperm[i] = perm[i];
+      if (tid == 0) {
+        const double nn = (double)len, mmv = (double)nv;
+        atomicAdd(&g_jac_flops[0], 8.0 * nn * nn * mmv + (56.0 / 3.0) * nn * nn * nn);
+        if (blockIdx.x == 0) {
+          const double dn = mode == 0 ? (double)w->n : (double)w->m, dm = mode == 0 ? (double)w->m : (double)w->n;
+          atomicAdd(&g_jac_flops[1], 8.0 * dn * dn * dm + (56.0 / 3.0) * dn * dn * dn);
+        }
+        if (nv >= 64) {
+          const long long t_now = clock64();
+          atomicAdd(&g_jac_dbg[5], (unsigned long long)(t_now - t_qr0));
+          atomicAdd(&g_jac_dbg[7], (unsigned long long)(t_now - t_start));
+        }
+      }
+      return;
+    }
+  }
   cplx* Z = SMEM ? Y : Yb;
   if (SMEM) {
     for (int e = tid; e < keff * ldz; e += JAC_THREADS) Z[e] = Yb[e];
@@ -548,6 +713,11 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   // ---- phase 4: spectrum + normalised right vectors Z[j][physical vector] ----
   __syncthreads();
   const long long t_jac1 = clock64();
+#ifdef OCMPS_JAC_TRACE
+  if (tid == 0 && nv >= 24)
+    printf("JT kind %d blk %d nv %d len %d keff %d qr %lld jac %lld tot %lld\n", a.kind, (int)blockIdx.x, nv, len, s_keff,
+           t_jac0 - t_qr0, t_jac1 - t_jac0, t_jac1 - t_start);
+#endif
   if (tid == 0 && nv >= 64) {
     atomicAdd(&g_jac_dbg[5], (unsigned long long)(t_jac0 - t_qr0));
     atomicAdd(&g_jac_dbg[6], (unsigned long long)(t_jac1 - t_jac0));
@@ -565,6 +735,89 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
         Ya[v * nv + (int)perm[c]] = make_double2(u.x * inv, u.y * inv);
       }
       __syncwarp();
+      if (lane == 0) b.P[B.p_off + v] = s;
+    } else if (lane == 0) {
+      b.P[B.p_off + v] = 0.0;
+    }
+  }
+}
+
+// Second half of the block decomposition for the blocks handed over by jacobi_blocks_kernel<true, true>: one-sided
+// Jacobi on the rows of R with the rows held in registers (jacobi_sweep_blocked), then spectrum and right vectors.
+__global__ void __launch_bounds__(JAC_THREADS) jacobi_rot_kernel(DecompArgs a, DecompBuffers b) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_rot, s_big;
+  __shared__ double s_nrm[JAC_BLOCKED_ROWS];
+  const DecompWork* w = b.dw;
+  if ((int)blockIdx.x >= w->nblocks) return;
+  const int keff = reinterpret_cast<const int*>(b.scratch_d + 7 * NV_MAX + OCMPS_MAX_BLK)[blockIdx.x];
+  if (keff < 0) return;                                   // finished by the first kernel
+  const DecompBlock B = w->blk[blockIdx.x];
+  const int nv = B.nv;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = JAC_THREADS / 32;
+  const int epl = (nv + 15) >> 4, ldz = epl << 4;
+  const double F = (b.scratch_d + 7 * NV_MAX)[blockIdx.x];
+  const double thr = F * DEFLATE_REL;
+  const short* perm = reinterpret_cast<const short*>(b.scratch_d + 4 * NV_MAX) + B.p_off;
+  cplx* Ya = b.ywork + B.ws_off;
+  const cplx* Yb = b.ywork + b.ywork_half + B.ws_off;
+  cplx* Z = reinterpret_cast<cplx*>(smem_raw);
+  double* nrm = s_nrm;
+  const long long t_jac0 = clock64();
+  for (int e = tid; e < keff * ldz; e += JAC_THREADS) Z[e] = Yb[e];
+  __syncthreads();
+  bool converged = false;
+  for (int sweep = 0; sweep < JAC_MAX_SWEEPS && !converged; ++sweep) {
+    for (int v = warp; v < keff; v += nwarps) {        // exact Gram diagonal at the start of every sweep
+      const cplx* y = Z + v * ldz;
+      double s = 0.0;
+      for (int c = lane; c < nv; c += 32) { cplx u = y[c]; s += u.x * u.x + u.y * u.y; }
+      s = warp_sum(s);
+      if (lane == 0) nrm[v] = s;
+    }
+    if (tid == 0) { s_rot = 0; s_big = 0; }
+    __syncthreads();
+    if (keff < 2) break;
+    switch (epl) {
+      case 1: jacobi_sweep_blocked<1>(Z, keff, nrm, thr, &s_rot, &s_big); break;
+      case 2: jacobi_sweep_blocked<2>(Z, keff, nrm, thr, &s_rot, &s_big); break;
+      case 3: jacobi_sweep_blocked<3>(Z, keff, nrm, thr, &s_rot, &s_big); break;
+      case 4: jacobi_sweep_blocked<4>(Z, keff, nrm, thr, &s_rot, &s_big); break;
+      case 5: jacobi_sweep_blocked<5>(Z, keff, nrm, thr, &s_rot, &s_big); break;
+      case 6: jacobi_sweep_blocked<6>(Z, keff, nrm, thr, &s_rot, &s_big); break;
+      case 7: jacobi_sweep_blocked<7>(Z, keff, nrm, thr, &s_rot, &s_big); break;
+      default: jacobi_sweep_blocked<8>(Z, keff, nrm, thr, &s_rot, &s_big); break;
+    }
+    // quadratic convergence: if every rotated pair had |<p|q>| < 1e-8 |p||q|, the residuals are now ~1e-16
+    converged = (s_rot == 0) || (s_big == 0);
+    if (tid == 0) { atomicAdd(&g_jac_dbg[0], 1ull); atomicMax(&g_jac_dbg[2], (unsigned long long)(sweep + 1)); if (nv >= 64) atomicAdd(&g_jac_dbg[3], 1ull); if (nv >= 64 && sweep == 0) atomicAdd(&g_jac_dbg[4], 1ull); }
+    __syncthreads();
+    if (!converged && sweep == JAC_MAX_SWEEPS - 1 && tid == 0) atomicOr(b.status, OCMPS_ST_NOCONV);
+  }
+  __syncthreads();
+  const long long t_jac1 = clock64();
+  if (tid == 0) {
+    atomicAdd(&g_jac_dbg[1], 1ull);
+    if (nv >= 64) {
+      atomicAdd(&g_jac_dbg[6], (unsigned long long)(t_jac1 - t_jac0));
+      atomicAdd(&g_jac_dbg[7], (unsigned long long)(t_jac1 - t_jac0));
+    }
+#ifdef OCMPS_JAC_TRACE
+    if (nv >= 24) printf("JT2 kind %d blk %d nv %d keff %d jac %lld\n", a.kind, (int)blockIdx.x, nv, keff, t_jac1 - t_jac0);
+#endif
+  }
+  // spectrum + normalised right vectors Z[j][physical vector]
+  for (int v = warp; v < nv; v += nwarps) {
+    if (v < keff) {
+      const cplx* y = Z + v * ldz;
+      double s = 0.0;
+      for (int c = lane; c < nv; c += 32) { cplx u = y[c]; s += u.x * u.x + u.y * u.y; }
+      s = warp_sum(s);
+      const double inv = s > 0.0 ? rsqrt(s) : 0.0;
+      for (int c = lane; c < nv; c += 32) {
+        cplx u = y[c];
+        Ya[v * nv + (int)perm[c]] = make_double2(u.x * inv, u.y * inv);
+      }
       if (lane == 0) b.P[B.p_off + v] = s;
     } else if (lane == 0) {
       b.P[B.p_off + v] = 0.0;
@@ -972,11 +1225,14 @@ void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_
     cudaFuncSetAttribute(jacobi_blocks_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(jacobi_blocks_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(build_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(jacobi_rot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(JAC_BLOCKED_ROWS * 16 * JAC_EPL * sizeof(cplx)));
     g_jac_attr_set[dev] = true;
   }
   jacobi_blocks_kernel<true, true><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
   if (long_rows) jacobi_blocks_kernel<true, false><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
   if (need_global) jacobi_blocks_kernel<false, false><<<nblk_launch, JAC_THREADS, 0, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
+  // (after ALL first-stage variants: each of them publishes the hand-over flag of the blocks it owns)
+  jacobi_rot_kernel<<<nblk_launch, JAC_THREADS, JAC_BLOCKED_ROWS * 16 * JAC_EPL * sizeof(cplx), s>>>(a, b);
 }
 
 void launch_truncate(const DecompArgs& a, const DecompBuffers& b, const TruncParams& tp, cudaStream_t s) {

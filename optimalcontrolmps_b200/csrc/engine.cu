@@ -411,7 +411,7 @@ void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int c
   launch_jacobi_blocks(a, ws->db, nblk, smem, need_global, long_rows, rank_tol, s);
   launch_truncate(a, ws->db, tp, s);
   launch_build_factors(a, ws->db, capK, capV, capC, s);
-  g_ocmps_launches += 4 + (need_global ? 1 : 0) + (long_rows ? 1 : 0);
+  g_ocmps_launches += 5 + (need_global ? 1 : 0) + (long_rows ? 1 : 0);
 }
 
 void phases_of(int D, double U, double tstep, double* re, double* im) {
