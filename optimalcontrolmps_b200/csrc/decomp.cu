@@ -99,10 +99,15 @@ __global__ void __launch_bounds__(SETUP_THREADS) decomp_setup_kernel(DecompArgs 
     cnt_c[q] = g.mode == 0 ? nr : nc;
   }
   __syncthreads();
+  // block charges lie between the smallest and the largest row charge (labels are sorted): only that range is scanned
+  int c_lo = chiL > 0 ? a.qL[0] : 0, c_hi = chiL > 0 ? a.qL[chiL - 1] + Drow - 1 : -1;
+  c_lo = c_lo < 0 ? 0 : c_lo;
+  c_hi = c_hi >= OCMPS_MAX_Q ? OCMPS_MAX_Q - 1 : c_hi;
+  if (tid < OCMPS_MAX_Q && (tid < c_lo || tid > c_hi)) blk_of_q[tid] = -1;
   if (tid == 0) {
     DecompWork* w = b.dw;
     int nb = 0, ov = 0, oc = 0, ows = 0;
-    for (int c = 0; c < OCMPS_MAX_Q; ++c) {
+    for (int c = c_lo; c <= c_hi; ++c) {
       int bid = -1;
       if (cnt_v[c] > 0 && cnt_c[c] > 0) {
         if (nb < OCMPS_MAX_BLK) {
@@ -328,6 +333,7 @@ template <bool SMEM, bool CACHED>
 __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a, DecompBuffers b, int smem_elems, double rank_tol) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_rot, s_keff, s_big;
+  __shared__ unsigned long long s_key[3];       // pivot keys of the QR steps j, j+1 and the one being reset
   __shared__ double s_F;
   __shared__ double s_nrm[JAC_NV_SMEM], s_nrm2[JAC_NV_SMEM], s_nrmref[JAC_NV_SMEM];
   __shared__ double s_rdr[JAC_NV_SMEM], s_rdi[JAC_NV_SMEM];   // diagonal of R
@@ -393,55 +399,60 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   const long long t_qr0 = clock64();
   // ---- phase 1: Householder QR with column pivoting, in place; R's strict upper part and rdiag remain ----
   // One barrier per step: the trailing norms and the position->slot map are double buffered, so the updates of
-  // step j (written to the "next" copies) cannot disturb a warp that is still selecting the pivot of step j.
+  // step j (written to the "next" copies) cannot disturb a warp that is still reading the pivot of step j.
   // Trailing norms are downdated (|y|^2 -= |r_ji|^2) and recomputed exactly only when cancellation has eaten
-  // half of the digits since the last exact value (the LAPACK xGEQP3 safeguard).
+  // half of the digits since the last exact value (the LAPACK xGEQP3 safeguard); they only SELECT the pivot, the
+  // reflector is built from the exact norm of the pivot vector.  The pivot of step j+1 is found while step j
+  // updates the norms: every update does an atomicMax on a (norm bits | position) key.
   const int kmax = nv < len ? nv : len;
   int keff = 0;
   double* ncur = nrm;  double* nnext = nrm2;
   short* pcur = permA; short* pnext = permB;
+  constexpr unsigned long long KEY_POS = 2047ull;        // low 11 bits: 2047 - position (ties -> smaller position)
+  if (tid < 3) s_key[tid] = 0ull;
+  __syncthreads();
+  for (int v = tid; v < nv; v += JAC_THREADS)
+    atomicMax(&s_key[0], ((unsigned long long)__double_as_longlong(nrm[v]) & ~KEY_POS) | (KEY_POS - (unsigned long long)v));
+  __syncthreads();
   for (int j = 0; j < kmax; ++j) {
-    // pivot: every warp finds the same argmax of the trailing norms (ties -> smaller position)
-    double best = -1.0; int bpos = j;
-    for (int i = j + lane; i < nv; i += 32) {
-      const double t = ncur[pcur[i]];
-      if (t > best) { best = t; bpos = i; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
-      if (ob > best || (ob == best && op < bpos)) { best = ob; bpos = op; }
-    }
-    if (!(best > rtol_abs)) break;         // numerical rank reached: the trailing block is negligible
-    keff = j + 1;
+    const int bpos = (int)(KEY_POS - (s_key[j % 3] & KEY_POS));
+    if (tid == 0) s_key[(j + 2) % 3] = 0ull;   // read last in step j-1, written next in step j+1
     const int pv = pcur[bpos];             // physical slot of the pivot vector
     const int pj = pcur[j];
     const cplx* x = Y + pv * len;          // Householder vector: x[j..len), with x[j] replaced by v0
-    const cplx alpha = x[j];
-    const double inx = rsqrt(best), normx = best * inx;
-    const double a2 = alpha.x * alpha.x + alpha.y * alpha.y;
-    const double ia = a2 > 0.0 ? rsqrt(a2) : 0.0, aabs = a2 * ia;
-    const double phr = a2 > 0.0 ? alpha.x * ia : 1.0, phi = a2 > 0.0 ? alpha.y * ia : 0.0;
-    const double v0r = alpha.x + phr * normx, v0i = alpha.y + phi * normx;
-    const double rb = rsqrt(normx * (normx + aabs));
-    const double beta = rb * rb;
-    if (tid == 0) { rdr[j] = -phr * normx; rdi[j] = -phi * normx; perm[j] = (short)pv; }   // R_jj; final position j
-    // apply H = I - beta v v^H to the remaining vectors, one half-warp per vector.  With at most 16*JAC_EPL
-    // components the Householder vector and the target vector live in registers (fully unrolled, uniform guards):
-    // the step is bound by instruction latency, so address arithmetic and loop overhead matter.
     const int nrem = len - j;                              // components j .. len-1
+    unsigned long long* knext = &s_key[(j + 1) % 3];
     if (CACHED && len <= 16 * JAC_EPL) {
+      // With at most 16*JAC_EPL components the Householder vector and the target vector live in registers (fully
+      // unrolled, uniform guards): the step is bound by instruction latency, so address arithmetic and loop overhead
+      // matter.  The reflector scalars (two dependent rsqrt) and the first dot product are independent chains:
+      // the dot product uses the raw pivot vector and is corrected for the replaced leading element afterwards.
       const int eplq = (nrem + 15) >> 4;
       cplx xv[JAC_EPL];
+      double sq0 = 0.0, sq1 = 0.0;
 #pragma unroll
       for (int e = 0; e < JAC_EPL; ++e) {
         if (e >= eplq) break;
         const int c = j + hl + 16 * e;
         xv[e] = make_double2(0.0, 0.0);
         if (c < len) xv[e] = x[c];
-        if (c == j) { xv[e].x = v0r; xv[e].y = v0i; }
+        const double q2 = xv[e].x * xv[e].x + xv[e].y * xv[e].y;
+        if (e & 1) sq1 += q2; else sq0 += q2;
       }
+      const double best = half_sum(sq0 + sq1);             // exact |x[j..len)|^2, identical in every half-warp
+      if (!(best > rtol_abs)) break;                       // numerical rank reached: the trailing block is negligible
+      keff = j + 1;
+      const double ax = __shfl_sync(0xffffffffu, xv[0].x, lane & 16), ay = __shfl_sync(0xffffffffu, xv[0].y, lane & 16);   // alpha = x[j]
+      const double inx = rsqrt(best), normx = best * inx;
+      const double a2 = ax * ax + ay * ay;
+      const double ia = a2 > 0.0 ? rsqrt(a2) : 0.0, aabs = a2 * ia;
+      const double phr = a2 > 0.0 ? ax * ia : 1.0, phi = a2 > 0.0 ? ay * ia : 0.0;
+      const double dr = phr * normx, di = phi * normx;     // v0 - alpha
+      const double rb = rsqrt(normx * (normx + aabs));
+      const double beta = rb * rb;
+      if (tid == 0) { rdr[j] = -dr; rdi[j] = -di; perm[j] = (short)pv; }   // R_jj; final position j
+      cplx x0p = xv[0];                                    // leading element of the reflector on its owner lane
+      if (hl == 0) { x0p.x += dr; x0p.y += di; }
       for (int ib = j + 1 + 2 * warp; ib < nv; ib += 2 * nwarps) {
         const int i = ib + half;
         const bool act = i < nv;
@@ -455,11 +466,14 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
           const int c = j + hl + 16 * e;
           yv[e] = make_double2(0.0, 0.0);
           if (act && c < len) yv[e] = y[c];
-          const double pr = xv[e].x * yv[e].x + xv[e].y * yv[e].y;      // conj(v) * y
+          const double pr = xv[e].x * yv[e].x + xv[e].y * yv[e].y;      // conj(x) * y
           const double pi = xv[e].x * yv[e].y - xv[e].y * yv[e].x;
           if (e & 1) { w1r += pr; w1i += pi; } else { w0r += pr; w0i += pi; }
         }
+        const double yjr = __shfl_sync(0xffffffffu, yv[0].x, lane & 16), yji = __shfl_sync(0xffffffffu, yv[0].y, lane & 16);
         double wr = half_sum(w0r + w1r), wi = half_sum(w0i + w1i);
+        wr += dr * yjr + di * yji;                           // + conj(v0 - alpha) * y_j
+        wi += dr * yji - di * yjr;
         const double fr = beta * wr, fi = beta * wi;
         double rji2 = 0.0;
 #pragma unroll
@@ -467,9 +481,10 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
           if (e >= eplq) break;
           const int c = j + hl + 16 * e;
           if (act && c < len) {
+            const cplx vv = e == 0 ? x0p : xv[e];
             cplx yy = yv[e];
-            yy.x -= fr * xv[e].x - fi * xv[e].y;
-            yy.y -= fr * xv[e].y + fi * xv[e].x;
+            yy.x -= fr * vv.x - fi * vv.y;
+            yy.y -= fr * vv.y + fi * vv.x;
             y[c] = yy;
             yv[e] = yy;
             if (e == 0 && hl == 0) rji2 = yy.x * yy.x + yy.y * yy.y;
@@ -492,9 +507,28 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
           tail = half_sum(tail);
           if (redo) { tnew = tail; if (hl == 0) nrmref[phys] = tail; }
         }
-        if (act && hl == 0) { nnext[phys] = tnew > 0.0 ? tnew : 0.0; pnext[i] = (short)phys; }
+        if (act && hl == 0) {
+          tnew = tnew > 0.0 ? tnew : 0.0;
+          nnext[phys] = tnew; pnext[i] = (short)phys;
+          atomicMax(knext, ((unsigned long long)__double_as_longlong(tnew) & ~KEY_POS) | (KEY_POS - (unsigned long long)i));
+        }
       }
     } else {
+    // generic path: every warp computes the exact norm of the pivot vector
+    double sq = 0.0;
+    for (int c = j + lane; c < len; c += 32) { const cplx u = x[c]; sq += u.x * u.x + u.y * u.y; }
+    const double best = warp_sum(sq);
+    if (!(best > rtol_abs)) break;
+    keff = j + 1;
+    const cplx alpha = x[j];
+    const double inx = rsqrt(best), normx = best * inx;
+    const double a2 = alpha.x * alpha.x + alpha.y * alpha.y;
+    const double ia = a2 > 0.0 ? rsqrt(a2) : 0.0, aabs = a2 * ia;
+    const double phr = a2 > 0.0 ? alpha.x * ia : 1.0, phi = a2 > 0.0 ? alpha.y * ia : 0.0;
+    const double v0r = alpha.x + phr * normx, v0i = alpha.y + phi * normx;
+    const double rb = rsqrt(normx * (normx + aabs));
+    const double beta = rb * rb;
+    if (tid == 0) { rdr[j] = -phr * normx; rdi[j] = -phi * normx; perm[j] = (short)pv; }   // R_jj; final position j
     for (int ib = j + 1 + 2 * warp; ib < nv; ib += 2 * nwarps) {
       const int i = ib + half;
       const bool act = i < nv;
@@ -537,7 +571,11 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
         tail = half_sum(tail);
         if (act && redo) { tnew = tail; if (hl == 0) nrmref[phys] = tail; }
       }
-      if (act && hl == 0) { nnext[phys] = tnew > 0.0 ? tnew : 0.0; pnext[i] = (short)phys; }
+      if (act && hl == 0) {
+        tnew = tnew > 0.0 ? tnew : 0.0;
+        nnext[phys] = tnew; pnext[i] = (short)phys;
+        atomicMax(knext, ((unsigned long long)__double_as_longlong(tnew) & ~KEY_POS) | (KEY_POS - (unsigned long long)i));
+      }
     }
     }
     __syncthreads();
