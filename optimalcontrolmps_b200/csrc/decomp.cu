@@ -326,6 +326,142 @@ __device__ __forceinline__ void jacobi_sweep_blocked(cplx* __restrict__ Z, int k
   }
 }
 
+// Householder QR with column pivoting of one block whose vectors have at most 16*EPL components (rows of Y, stride
+// len), one half-warp per vector and EPL components per lane at the fixed positions c = hl + 16 e: addresses are
+// immediates and the loops are unrolled exactly (the step is bound by instruction issue, not by arithmetic).
+// Chunks of 16 components that lie entirely above the diagonal are skipped with uniform branches; inside the chunk of
+// the diagonal the reflector is zero above it, so those lanes compute y -= f * 0.
+//  * The reflector is built from the exact norm of the pivot vector; the downdated norms only select pivots.
+//  * The dot products use the raw pivot vector and are corrected for the replaced diagonal element afterwards, so
+//    the reflector scalars (two dependent rsqrt) and the first dot product are independent chains.
+//  * The pivot of step j+1: every half-warp leaves the best (norm bits | 2047 - position) key of the vectors it
+//    updated in s_cand; a step starts with two REDUX over the 32 candidates.
+// Returns the numerical rank; ncur / pcur are left pointing at the final trailing norms / position -> slot map.
+template <int EPL>
+__device__ __forceinline__ int qr_pivoted_cached(cplx* __restrict__ Y, int nv, int len, double rtol_abs, double*& ncur, double*& nnext,
+                                                 double* __restrict__ nrmref, double* __restrict__ rdr, double* __restrict__ rdi,
+                                                 short* __restrict__ perm, short*& pcur, short*& pnext,
+                                                 unsigned long long (*s_cand)[32]) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = lane >> 4, hl = lane & 15;
+  constexpr int nwarps = JAC_THREADS / 32;
+  constexpr unsigned long long KEY_POS = 2047ull;
+  const int kmax = nv < len ? nv : len;
+  int keff = 0;
+  if (warp == 0) {
+    unsigned long long k = 0ull;
+    for (int v = lane; v < nv; v += 32) {
+      const unsigned long long kv = ((unsigned long long)__double_as_longlong(ncur[v]) & ~KEY_POS) | (KEY_POS - (unsigned long long)v);
+      k = kv > k ? kv : k;
+    }
+    s_cand[0][lane] = k;
+  }
+  __syncthreads();
+  for (int j = 0; j < kmax; ++j) {
+    const int e0 = j >> 4;
+    int bpos;
+    {
+      const unsigned long long kk = s_cand[j & 1][lane];
+      const unsigned khi = (unsigned)(kk >> 32);
+      const unsigned mhi = __reduce_max_sync(0xffffffffu, khi);
+      const unsigned mlo = __reduce_max_sync(0xffffffffu, khi == mhi ? (unsigned)kk : 0u);
+      bpos = (int)(KEY_POS - (unsigned long long)(mlo & 2047u));
+    }
+    const int pv = pcur[bpos];             // physical slot of the pivot vector
+    const int pj = pcur[j];
+    const cplx* x = Y + pv * len;
+    const cplx alpha = x[j];
+    cplx xv[EPL];
+    double sq0 = 0.0, sq1 = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      xv[e] = make_double2(0.0, 0.0);
+      if (e >= e0) {
+        const int c = hl + 16 * e;
+        if (c >= j && (e < EPL - 1 || c < len)) xv[e] = x[c];
+        const double q2 = xv[e].x * xv[e].x + xv[e].y * xv[e].y;
+        if (e & 1) sq1 += q2; else sq0 += q2;
+      }
+    }
+    const double best = half_sum(sq0 + sq1);             // exact |x[j..len)|^2, bitwise identical in every half-warp
+    if (!(best > rtol_abs)) break;                       // numerical rank reached: the trailing block is negligible
+    keff = j + 1;
+    const double inx = rsqrt(best), normx = best * inx;
+    const double a2 = alpha.x * alpha.x + alpha.y * alpha.y;
+    const double ia = a2 > 0.0 ? rsqrt(a2) : 0.0, aabs = a2 * ia;
+    const double phr = a2 > 0.0 ? alpha.x * ia : 1.0, phi = a2 > 0.0 ? alpha.y * ia : 0.0;
+    const double dr = phr * normx, di = phi * normx;     // v0 - alpha
+    const double v0r = alpha.x + dr, v0i = alpha.y + di;
+    const double rb = rsqrt(normx * (normx + aabs));
+    const double beta = rb * rb;
+    if (tid == 0) { rdr[j] = -dr; rdi[j] = -di; perm[j] = (short)pv; }   // R_jj; final position j
+    unsigned long long cand = 0ull;
+    for (int ib = j + 1 + 2 * warp; ib < nv; ib += 2 * nwarps) {
+      const int i = ib + half;
+      const bool act = i < nv;
+      const int phys = act ? (i == bpos ? pj : (int)pcur[i]) : pv;
+      cplx* y = Y + phys * len;
+      const cplx yj = y[j];
+      const double told = ncur[phys], tref = nrmref[phys];
+      cplx yv[EPL];
+      double w0r = 0.0, w0i = 0.0, w1r = 0.0, w1i = 0.0;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        if (e >= e0) {
+          const int c = hl + 16 * e;
+          yv[e] = make_double2(0.0, 0.0);
+          if (e < EPL - 1 || c < len) yv[e] = y[c];
+          const double pr = xv[e].x * yv[e].x + xv[e].y * yv[e].y;      // conj(x) * y
+          const double pi = xv[e].x * yv[e].y - xv[e].y * yv[e].x;
+          if (e & 1) { w1r += pr; w1i += pi; } else { w0r += pr; w0i += pi; }
+        }
+      }
+      double wr = half_sum(w0r + w1r), wi = half_sum(w0i + w1i);
+      wr += dr * yj.x + di * yj.y;                           // + conj(v0 - alpha) * y_j
+      wi += dr * yj.y - di * yj.x;
+      const double fr = beta * wr, fi = beta * wi;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        if (e >= e0) {
+          const int c = hl + 16 * e;
+          cplx yy = yv[e];
+          yy.x -= fr * xv[e].x - fi * xv[e].y;
+          yy.y -= fr * xv[e].y + fi * xv[e].x;
+          yv[e] = yy;
+          if (act && (e < EPL - 1 || c < len)) y[c] = yy;
+        }
+      }
+      // the diagonal component sees v0 instead of alpha: its owner lane overwrites what the loop stored
+      const double yjr = yj.x - (fr * v0r - fi * v0i), yji = yj.y - (fr * v0i + fi * v0r);
+      if (act && hl == (j & 15)) y[j] = make_double2(yjr, yji);
+      const double rji2 = yjr * yjr + yji * yji;
+      double tnew = told - rji2;
+      const bool redo = act && !(tnew > 1.5e-8 * tref);
+      if (__any_sync(0xffffffffu, redo)) {                   // rare: exact trailing norm
+        double tail = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          if (e >= e0) {
+            const int c = hl + 16 * e;
+            if (c > j) tail += yv[e].x * yv[e].x + yv[e].y * yv[e].y;
+          }
+        }
+        tail = half_sum(tail);
+        if (redo) { tnew = tail; if (hl == 0) nrmref[phys] = tail; }
+      }
+      if (act) {
+        tnew = tnew > 0.0 ? tnew : 0.0;
+        if (hl == 0) { nnext[phys] = tnew; pnext[i] = (short)phys; }
+        const unsigned long long kv = ((unsigned long long)__double_as_longlong(tnew) & ~KEY_POS) | (KEY_POS - (unsigned long long)i);
+        cand = kv > cand ? kv : cand;
+      }
+    }
+    if (hl == 0) s_cand[(j + 1) & 1][2 * warp + half] = cand;
+    __syncthreads();
+    { double* t = ncur; ncur = nnext; nnext = t; short* u = pcur; pcur = pnext; pnext = u; }
+  }
+  return keff;
+}
+
 // SMEM: the block lives in shared memory (else in the global scratch); CACHED: rows are at most 16*JAC_EPL long and a
 // pair's elements stay in registers between the dot product and the rotation.  A block is handled by exactly one
 // instantiation; splitting them keeps the hot loop of the common case small enough for the instruction caches.
@@ -333,7 +469,8 @@ template <bool SMEM, bool CACHED>
 __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a, DecompBuffers b, int smem_elems, double rank_tol) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_rot, s_keff, s_big;
-  __shared__ unsigned long long s_key[3];       // pivot keys of the QR steps j, j+1 and the one being reset
+  __shared__ unsigned long long s_key[3];       // pivot keys of the QR steps j, j+1 and the one being reset (generic path)
+  __shared__ unsigned long long s_cand[2][32];  // per half-warp pivot candidates of the steps j, j+1 (cached path)
   __shared__ double s_F;
   __shared__ double s_nrm[JAC_NV_SMEM], s_nrm2[JAC_NV_SMEM], s_nrmref[JAC_NV_SMEM];
   __shared__ double s_rdr[JAC_NV_SMEM], s_rdi[JAC_NV_SMEM];   // diagonal of R
@@ -409,12 +546,25 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   double* ncur = nrm;  double* nnext = nrm2;
   short* pcur = permA; short* pnext = permB;
   constexpr unsigned long long KEY_POS = 2047ull;        // low 11 bits: 2047 - position (ties -> smaller position)
+  const bool qr_cached = CACHED && len <= 16 * JAC_EPL;
+  if (qr_cached) {
+    switch ((len + 15) >> 4) {
+      case 1: keff = qr_pivoted_cached<1>(Y, nv, len, rtol_abs, ncur, nnext, nrmref, rdr, rdi, perm, pcur, pnext, s_cand); break;
+      case 2: keff = qr_pivoted_cached<2>(Y, nv, len, rtol_abs, ncur, nnext, nrmref, rdr, rdi, perm, pcur, pnext, s_cand); break;
+      case 3: keff = qr_pivoted_cached<3>(Y, nv, len, rtol_abs, ncur, nnext, nrmref, rdr, rdi, perm, pcur, pnext, s_cand); break;
+      case 4: keff = qr_pivoted_cached<4>(Y, nv, len, rtol_abs, ncur, nnext, nrmref, rdr, rdi, perm, pcur, pnext, s_cand); break;
+      case 5: keff = qr_pivoted_cached<5>(Y, nv, len, rtol_abs, ncur, nnext, nrmref, rdr, rdi, perm, pcur, pnext, s_cand); break;
+      case 6: keff = qr_pivoted_cached<6>(Y, nv, len, rtol_abs, ncur, nnext, nrmref, rdr, rdi, perm, pcur, pnext, s_cand); break;
+      case 7: keff = qr_pivoted_cached<7>(Y, nv, len, rtol_abs, ncur, nnext, nrmref, rdr, rdi, perm, pcur, pnext, s_cand); break;
+      default: keff = qr_pivoted_cached<8>(Y, nv, len, rtol_abs, ncur, nnext, nrmref, rdr, rdi, perm, pcur, pnext, s_cand); break;
+    }
+  }
   if (tid < 3) s_key[tid] = 0ull;
   __syncthreads();
   for (int v = tid; v < nv; v += JAC_THREADS)
     atomicMax(&s_key[0], ((unsigned long long)__double_as_longlong(nrm[v]) & ~KEY_POS) | (KEY_POS - (unsigned long long)v));
   __syncthreads();
-  for (int j = 0; j < kmax; ++j) {
+  for (int j = 0; j < (qr_cached ? 0 : kmax); ++j) {
     const int bpos = (int)(KEY_POS - (s_key[j % 3] & KEY_POS));
     if (tid == 0) s_key[(j + 2) % 3] = 0ull;   // read last in step j-1, written next in step j+1
     const int pv = pcur[bpos];             // physical slot of the pivot vector
@@ -422,98 +572,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
     const cplx* x = Y + pv * len;          // Householder vector: x[j..len), with x[j] replaced by v0
     const int nrem = len - j;                              // components j .. len-1
     unsigned long long* knext = &s_key[(j + 1) % 3];
-    if (CACHED && len <= 16 * JAC_EPL) {
-      // With at most 16*JAC_EPL components the Householder vector and the target vector live in registers (fully
-      // unrolled, uniform guards): the step is bound by instruction latency, so address arithmetic and loop overhead
-      // matter.  The reflector scalars (two dependent rsqrt) and the first dot product are independent chains:
-      // the dot product uses the raw pivot vector and is corrected for the replaced leading element afterwards.
-      const int eplq = (nrem + 15) >> 4;
-      cplx xv[JAC_EPL];
-      double sq0 = 0.0, sq1 = 0.0;
-#pragma unroll
-      for (int e = 0; e < JAC_EPL; ++e) {
-        if (e >= eplq) break;
-        const int c = j + hl + 16 * e;
-        xv[e] = make_double2(0.0, 0.0);
-        if (c < len) xv[e] = x[c];
-        const double q2 = xv[e].x * xv[e].x + xv[e].y * xv[e].y;
-        if (e & 1) sq1 += q2; else sq0 += q2;
-      }
-      const double best = half_sum(sq0 + sq1);             // exact |x[j..len)|^2, identical in every half-warp
-      if (!(best > rtol_abs)) break;                       // numerical rank reached: the trailing block is negligible
-      keff = j + 1;
-      const double ax = __shfl_sync(0xffffffffu, xv[0].x, lane & 16), ay = __shfl_sync(0xffffffffu, xv[0].y, lane & 16);   // alpha = x[j]
-      const double inx = rsqrt(best), normx = best * inx;
-      const double a2 = ax * ax + ay * ay;
-      const double ia = a2 > 0.0 ? rsqrt(a2) : 0.0, aabs = a2 * ia;
-      const double phr = a2 > 0.0 ? ax * ia : 1.0, phi = a2 > 0.0 ? ay * ia : 0.0;
-      const double dr = phr * normx, di = phi * normx;     // v0 - alpha
-      const double rb = rsqrt(normx * (normx + aabs));
-      const double beta = rb * rb;
-      if (tid == 0) { rdr[j] = -dr; rdi[j] = -di; perm[j] = (short)pv; }   // R_jj; final position j
-      cplx x0p = xv[0];                                    // leading element of the reflector on its owner lane
-      if (hl == 0) { x0p.x += dr; x0p.y += di; }
-      for (int ib = j + 1 + 2 * warp; ib < nv; ib += 2 * nwarps) {
-        const int i = ib + half;
-        const bool act = i < nv;
-        const int phys = act ? (i == bpos ? pj : (int)pcur[i]) : pv;
-        cplx* y = Y + phys * len;
-        cplx yv[JAC_EPL];
-        double w0r = 0.0, w0i = 0.0, w1r = 0.0, w1i = 0.0;
-#pragma unroll
-        for (int e = 0; e < JAC_EPL; ++e) {
-          if (e >= eplq) break;
-          const int c = j + hl + 16 * e;
-          yv[e] = make_double2(0.0, 0.0);
-          if (act && c < len) yv[e] = y[c];
-          const double pr = xv[e].x * yv[e].x + xv[e].y * yv[e].y;      // conj(x) * y
-          const double pi = xv[e].x * yv[e].y - xv[e].y * yv[e].x;
-          if (e & 1) { w1r += pr; w1i += pi; } else { w0r += pr; w0i += pi; }
-        }
-        const double yjr = __shfl_sync(0xffffffffu, yv[0].x, lane & 16), yji = __shfl_sync(0xffffffffu, yv[0].y, lane & 16);
-        double wr = half_sum(w0r + w1r), wi = half_sum(w0i + w1i);
-        wr += dr * yjr + di * yji;                           // + conj(v0 - alpha) * y_j
-        wi += dr * yji - di * yjr;
-        const double fr = beta * wr, fi = beta * wi;
-        double rji2 = 0.0;
-#pragma unroll
-        for (int e = 0; e < JAC_EPL; ++e) {
-          if (e >= eplq) break;
-          const int c = j + hl + 16 * e;
-          if (act && c < len) {
-            const cplx vv = e == 0 ? x0p : xv[e];
-            cplx yy = yv[e];
-            yy.x -= fr * vv.x - fi * vv.y;
-            yy.y -= fr * vv.y + fi * vv.x;
-            y[c] = yy;
-            yv[e] = yy;
-            if (e == 0 && hl == 0) rji2 = yy.x * yy.x + yy.y * yy.y;
-          }
-        }
-        rji2 = __shfl_sync(0xffffffffu, rji2, lane & 16);     // component j is owned by lane 0 of the half-warp
-        double tnew = 0.0;
-        bool redo = false;
-        if (act) { tnew = ncur[phys] - rji2; redo = !(tnew > 1.5e-8 * nrmref[phys]); }
-        if (__any_sync(0xffffffffu, redo)) {                   // rare: exact trailing norm
-          double tail = 0.0;
-          if (redo) {
-#pragma unroll
-            for (int e = 0; e < JAC_EPL; ++e) {
-              if (e >= eplq) break;
-              const int c = j + hl + 16 * e;
-              if (c > j && c < len) tail += yv[e].x * yv[e].x + yv[e].y * yv[e].y;
-            }
-          }
-          tail = half_sum(tail);
-          if (redo) { tnew = tail; if (hl == 0) nrmref[phys] = tail; }
-        }
-        if (act && hl == 0) {
-          tnew = tnew > 0.0 ? tnew : 0.0;
-          nnext[phys] = tnew; pnext[i] = (short)phys;
-          atomicMax(knext, ((unsigned long long)__double_as_longlong(tnew) & ~KEY_POS) | (KEY_POS - (unsigned long long)i));
-        }
-      }
-    } else {
+    {
     // generic path: every warp computes the exact norm of the pivot vector
     double sq = 0.0;
     for (int c = j + lane; c < len; c += 32) { const cplx u = x[c]; sq += u.x * u.x + u.y * u.y; }
