@@ -327,137 +327,156 @@ __device__ __forceinline__ void jacobi_sweep_blocked(cplx* __restrict__ Z, int k
 }
 
 // Householder QR with column pivoting of one block whose vectors have at most 16*EPL components (rows of Y, stride
-// len), one half-warp per vector and EPL components per lane at the fixed positions c = hl + 16 e: addresses are
-// immediates and the loops are unrolled exactly (the step is bound by instruction issue, not by arithmetic).
-// Chunks of 16 components that lie entirely above the diagonal are skipped with uniform branches; inside the chunk of
-// the diagonal the reflector is zero above it, so those lanes compute y -= f * 0.
+// len), one half-warp per vector and EPL components per lane at the fixed positions c = hl + 16 e.  A step is bound by
+// instruction issue, not by arithmetic, so everything is specialised at compile time: EPL (addresses are immediates)
+// and E0 = j / 16, the first chunk of 16 components that still takes part (chunks above the diagonal are not touched;
+// inside the chunk of the diagonal the reflector is zero above it, so those lanes compute y -= f * 0).
 //  * The reflector is built from the exact norm of the pivot vector; the downdated norms only select pivots.
 //  * The dot products use the raw pivot vector and are corrected for the replaced diagonal element afterwards, so
 //    the reflector scalars (two dependent rsqrt) and the first dot product are independent chains.
 //  * The pivot of step j+1: every half-warp leaves the best (norm bits | 2047 - position) key of the vectors it
 //    updated in s_cand; a step starts with two REDUX over the 32 candidates.
-// Returns the numerical rank; ncur / pcur are left pointing at the final trailing norms / position -> slot map.
-template <int EPL>
-__device__ __forceinline__ int qr_pivoted_cached(cplx* __restrict__ Y, int nv, int len, double rtol_abs, double*& ncur, double*& nnext,
-                                                 double* __restrict__ nrmref, double* __restrict__ rdr, double* __restrict__ rdi,
-                                                 short* __restrict__ perm, short*& pcur, short*& pnext,
-                                                 unsigned long long (*s_cand)[32]) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = lane >> 4, hl = lane & 15;
-  constexpr int nwarps = JAC_THREADS / 32;
+struct QrState {
+  cplx* Y;
+  int nv, len;
+  double rtol_abs;
+  double *ncur, *nnext, *nrmref, *rdr, *rdi;
+  short *perm, *pcur, *pnext;
+  unsigned long long (*s_cand)[32];
+};
+
+// One step; false when the numerical rank is reached (nothing was changed then).
+template <int EPL, int E0>
+__device__ __forceinline__ bool qr_step_cached(const QrState& q, int j) {
   constexpr unsigned long long KEY_POS = 2047ull;
-  const int kmax = nv < len ? nv : len;
-  int keff = 0;
+  constexpr int nwarps = JAC_THREADS / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = lane >> 4, hl = lane & 15;
+  const int len = q.len, nv = q.nv;
+  int bpos;
+  {
+    const unsigned long long kk = q.s_cand[j & 1][lane];
+    const unsigned khi = (unsigned)(kk >> 32);
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, khi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, khi == mhi ? (unsigned)kk : 0u);
+    bpos = (int)(KEY_POS - (unsigned long long)(mlo & 2047u));
+  }
+  const int pv = q.pcur[bpos];             // physical slot of the pivot vector
+  const int pj = q.pcur[j];
+  const cplx* x = q.Y + pv * len;
+  const cplx alpha = x[j];
+  cplx xv[EPL];
+  double sq0 = 0.0, sq1 = 0.0;
+#pragma unroll
+  for (int e = E0; e < EPL; ++e) {
+    const int c = hl + 16 * e;
+    const bool in = (e > E0 || c >= j) && (e < EPL - 1 || c < len);
+    xv[e] = x[in ? c : j];
+    if (!in) xv[e] = make_double2(0.0, 0.0);
+    const double q2 = xv[e].x * xv[e].x + xv[e].y * xv[e].y;
+    if ((e - E0) & 1) sq1 += q2; else sq0 += q2;
+  }
+  const double best = half_sum(sq0 + sq1);             // exact |x[j..len)|^2, bitwise identical in every half-warp
+  if (!(best > q.rtol_abs)) return false;              // numerical rank reached: the trailing block is negligible
+  const double inx = rsqrt(best), normx = best * inx;
+  const double a2 = alpha.x * alpha.x + alpha.y * alpha.y;
+  const double ia = a2 > 0.0 ? rsqrt(a2) : 0.0, aabs = a2 * ia;
+  const double phr = a2 > 0.0 ? alpha.x * ia : 1.0, phi = a2 > 0.0 ? alpha.y * ia : 0.0;
+  const double dr = phr * normx, di = phi * normx;     // v0 - alpha
+  const double v0r = alpha.x + dr, v0i = alpha.y + di;
+  const double rb = rsqrt(normx * (normx + aabs));
+  const double beta = rb * rb;
+  if (tid == 0) { q.rdr[j] = -dr; q.rdi[j] = -di; q.perm[j] = (short)pv; }   // R_jj; final position j
+  unsigned long long cand = 0ull;
+  for (int ib = j + 1 + 2 * warp; ib < nv; ib += 2 * nwarps) {
+    const int i = ib + half;
+    const bool act = i < nv;
+    const int phys = act ? (i == bpos ? pj : (int)q.pcur[i]) : pv;
+    cplx* y = q.Y + phys * len;
+    const cplx yj = y[j];
+    const double told = q.ncur[phys], tref = q.nrmref[phys];
+    cplx yv[EPL];
+    double w0r = 0.0, w0i = 0.0, w1r = 0.0, w1i = 0.0;
+#pragma unroll
+    for (int e = E0; e < EPL; ++e) {
+      const int c = hl + 16 * e;
+      if (e < EPL - 1) yv[e] = y[c];
+      else { yv[e] = y[c < len ? c : j]; if (c >= len) yv[e] = make_double2(0.0, 0.0); }
+      const double pr = xv[e].x * yv[e].x + xv[e].y * yv[e].y;      // conj(x) * y
+      const double pi = xv[e].x * yv[e].y - xv[e].y * yv[e].x;
+      if ((e - E0) & 1) { w1r += pr; w1i += pi; } else { w0r += pr; w0i += pi; }
+    }
+    double wr = half_sum(w0r + w1r), wi = half_sum(w0i + w1i);
+    wr += dr * yj.x + di * yj.y;                           // + conj(v0 - alpha) * y_j
+    wi += dr * yj.y - di * yj.x;
+    const double fr = beta * wr, fi = beta * wi;
+#pragma unroll
+    for (int e = E0; e < EPL; ++e) {
+      const int c = hl + 16 * e;
+      cplx yy = yv[e];
+      yy.x -= fr * xv[e].x - fi * xv[e].y;
+      yy.y -= fr * xv[e].y + fi * xv[e].x;
+      yv[e] = yy;
+      if (act && (e < EPL - 1 || c < len)) y[c] = yy;
+    }
+    // the diagonal component sees v0 instead of alpha: its owner lane overwrites what the loop stored
+    const double yjr = yj.x - (fr * v0r - fi * v0i), yji = yj.y - (fr * v0i + fi * v0r);
+    if (act && hl == (j & 15)) y[j] = make_double2(yjr, yji);
+    const double rji2 = yjr * yjr + yji * yji;
+    double tnew = told - rji2;
+    const bool redo = act && !(tnew > 1.5e-8 * tref);
+    if (__any_sync(0xffffffffu, redo)) {                   // rare: exact trailing norm
+      double tail = 0.0;
+#pragma unroll
+      for (int e = E0; e < EPL; ++e) {
+        const int c = hl + 16 * e;
+        if (e > E0 || c > j) tail += yv[e].x * yv[e].x + yv[e].y * yv[e].y;
+      }
+      tail = half_sum(tail);
+      if (redo) { tnew = tail; if (hl == 0) q.nrmref[phys] = tail; }
+    }
+    if (act) {
+      tnew = tnew > 0.0 ? tnew : 0.0;
+      if (hl == 0) { q.nnext[phys] = tnew; q.pnext[i] = (short)phys; }
+      const unsigned long long kv = ((unsigned long long)__double_as_longlong(tnew) & ~KEY_POS) | (KEY_POS - (unsigned long long)i);
+      cand = kv > cand ? kv : cand;
+    }
+  }
+  if (hl == 0) q.s_cand[(j + 1) & 1][2 * warp + half] = cand;
+  return true;
+}
+
+// Returns the numerical rank; q.ncur / q.pcur are left pointing at the final trailing norms / position -> slot map.
+template <int EPL>
+__device__ __forceinline__ int qr_pivoted_cached(QrState& q) {
+  constexpr unsigned long long KEY_POS = 2047ull;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kmax = q.nv < q.len ? q.nv : q.len;
   if (warp == 0) {
     unsigned long long k = 0ull;
-    for (int v = lane; v < nv; v += 32) {
-      const unsigned long long kv = ((unsigned long long)__double_as_longlong(ncur[v]) & ~KEY_POS) | (KEY_POS - (unsigned long long)v);
+    for (int v = lane; v < q.nv; v += 32) {
+      const unsigned long long kv = ((unsigned long long)__double_as_longlong(q.ncur[v]) & ~KEY_POS) | (KEY_POS - (unsigned long long)v);
       k = kv > k ? kv : k;
     }
-    s_cand[0][lane] = k;
+    q.s_cand[0][lane] = k;
   }
   __syncthreads();
+  int keff = 0;
   for (int j = 0; j < kmax; ++j) {
-    const int e0 = j >> 4;
-    int bpos;
-    {
-      const unsigned long long kk = s_cand[j & 1][lane];
-      const unsigned khi = (unsigned)(kk >> 32);
-      const unsigned mhi = __reduce_max_sync(0xffffffffu, khi);
-      const unsigned mlo = __reduce_max_sync(0xffffffffu, khi == mhi ? (unsigned)kk : 0u);
-      bpos = (int)(KEY_POS - (unsigned long long)(mlo & 2047u));
+    bool ok = false;
+    switch (j >> 4) {
+      case 0: ok = qr_step_cached<EPL, 0>(q, j); break;
+      case 1: if constexpr (EPL > 1) ok = qr_step_cached<EPL, 1>(q, j); break;
+      case 2: if constexpr (EPL > 2) ok = qr_step_cached<EPL, 2>(q, j); break;
+      case 3: if constexpr (EPL > 3) ok = qr_step_cached<EPL, 3>(q, j); break;
+      case 4: if constexpr (EPL > 4) ok = qr_step_cached<EPL, 4>(q, j); break;
+      case 5: if constexpr (EPL > 5) ok = qr_step_cached<EPL, 5>(q, j); break;
+      case 6: if constexpr (EPL > 6) ok = qr_step_cached<EPL, 6>(q, j); break;
+      default: if constexpr (EPL > 7) ok = qr_step_cached<EPL, 7>(q, j); break;
     }
-    const int pv = pcur[bpos];             // physical slot of the pivot vector
-    const int pj = pcur[j];
-    const cplx* x = Y + pv * len;
-    const cplx alpha = x[j];
-    cplx xv[EPL];
-    double sq0 = 0.0, sq1 = 0.0;
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) {
-      xv[e] = make_double2(0.0, 0.0);
-      if (e >= e0) {
-        const int c = hl + 16 * e;
-        if (c >= j && (e < EPL - 1 || c < len)) xv[e] = x[c];
-        const double q2 = xv[e].x * xv[e].x + xv[e].y * xv[e].y;
-        if (e & 1) sq1 += q2; else sq0 += q2;
-      }
-    }
-    const double best = half_sum(sq0 + sq1);             // exact |x[j..len)|^2, bitwise identical in every half-warp
-    if (!(best > rtol_abs)) break;                       // numerical rank reached: the trailing block is negligible
+    if (!ok) break;
     keff = j + 1;
-    const double inx = rsqrt(best), normx = best * inx;
-    const double a2 = alpha.x * alpha.x + alpha.y * alpha.y;
-    const double ia = a2 > 0.0 ? rsqrt(a2) : 0.0, aabs = a2 * ia;
-    const double phr = a2 > 0.0 ? alpha.x * ia : 1.0, phi = a2 > 0.0 ? alpha.y * ia : 0.0;
-    const double dr = phr * normx, di = phi * normx;     // v0 - alpha
-    const double v0r = alpha.x + dr, v0i = alpha.y + di;
-    const double rb = rsqrt(normx * (normx + aabs));
-    const double beta = rb * rb;
-    if (tid == 0) { rdr[j] = -dr; rdi[j] = -di; perm[j] = (short)pv; }   // R_jj; final position j
-    unsigned long long cand = 0ull;
-    for (int ib = j + 1 + 2 * warp; ib < nv; ib += 2 * nwarps) {
-      const int i = ib + half;
-      const bool act = i < nv;
-      const int phys = act ? (i == bpos ? pj : (int)pcur[i]) : pv;
-      cplx* y = Y + phys * len;
-      const cplx yj = y[j];
-      const double told = ncur[phys], tref = nrmref[phys];
-      cplx yv[EPL];
-      double w0r = 0.0, w0i = 0.0, w1r = 0.0, w1i = 0.0;
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) {
-        if (e >= e0) {
-          const int c = hl + 16 * e;
-          yv[e] = make_double2(0.0, 0.0);
-          if (e < EPL - 1 || c < len) yv[e] = y[c];
-          const double pr = xv[e].x * yv[e].x + xv[e].y * yv[e].y;      // conj(x) * y
-          const double pi = xv[e].x * yv[e].y - xv[e].y * yv[e].x;
-          if (e & 1) { w1r += pr; w1i += pi; } else { w0r += pr; w0i += pi; }
-        }
-      }
-      double wr = half_sum(w0r + w1r), wi = half_sum(w0i + w1i);
-      wr += dr * yj.x + di * yj.y;                           // + conj(v0 - alpha) * y_j
-      wi += dr * yj.y - di * yj.x;
-      const double fr = beta * wr, fi = beta * wi;
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) {
-        if (e >= e0) {
-          const int c = hl + 16 * e;
-          cplx yy = yv[e];
-          yy.x -= fr * xv[e].x - fi * xv[e].y;
-          yy.y -= fr * xv[e].y + fi * xv[e].x;
-          yv[e] = yy;
-          if (act && (e < EPL - 1 || c < len)) y[c] = yy;
-        }
-      }
-      // the diagonal component sees v0 instead of alpha: its owner lane overwrites what the loop stored
-      const double yjr = yj.x - (fr * v0r - fi * v0i), yji = yj.y - (fr * v0i + fi * v0r);
-      if (act && hl == (j & 15)) y[j] = make_double2(yjr, yji);
-      const double rji2 = yjr * yjr + yji * yji;
-      double tnew = told - rji2;
-      const bool redo = act && !(tnew > 1.5e-8 * tref);
-      if (__any_sync(0xffffffffu, redo)) {                   // rare: exact trailing norm
-        double tail = 0.0;
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) {
-          if (e >= e0) {
-            const int c = hl + 16 * e;
-            if (c > j) tail += yv[e].x * yv[e].x + yv[e].y * yv[e].y;
-          }
-        }
-        tail = half_sum(tail);
-        if (redo) { tnew = tail; if (hl == 0) nrmref[phys] = tail; }
-      }
-      if (act) {
-        tnew = tnew > 0.0 ? tnew : 0.0;
-        if (hl == 0) { nnext[phys] = tnew; pnext[i] = (short)phys; }
-        const unsigned long long kv = ((unsigned long long)__double_as_longlong(tnew) & ~KEY_POS) | (KEY_POS - (unsigned long long)i);
-        cand = kv > cand ? kv : cand;
-      }
-    }
-    if (hl == 0) s_cand[(j + 1) & 1][2 * warp + half] = cand;
     __syncthreads();
-    { double* t = ncur; ncur = nnext; nnext = t; short* u = pcur; pcur = pnext; pnext = u; }
+    { double* t = q.ncur; q.ncur = q.nnext; q.nnext = t; short* u = q.pcur; q.pcur = q.pnext; q.pnext = u; }
   }
   return keff;
 }
@@ -548,16 +567,21 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   constexpr unsigned long long KEY_POS = 2047ull;        // low 11 bits: 2047 - position (ties -> smaller position)
   const bool qr_cached = CACHED && len <= 16 * JAC_EPL;
   if (qr_cached) {
+    QrState q;
+    q.Y = Y; q.nv = nv; q.len = len; q.rtol_abs = rtol_abs;
+    q.ncur = ncur; q.nnext = nnext; q.nrmref = nrmref; q.rdr = rdr; q.rdi = rdi;
+    q.perm = perm; q.pcur = pcur; q.pnext = pnext; q.s_cand = s_cand;
     switch ((len + 15) >> 4) {
-      case 1: keff = qr_pivoted_cached<1>(Y, nv, len, rtol_abs, ncur, nnext, nrmref, rdr, rdi, perm, pcur, pnext, s_cand); break;
-      case 2: keff = qr_pivoted_cached<2>(Y, nv, len, rtol_abs, ncur, nnext, nrmref, rdr, rdi, perm, pcur, pnext, s_cand); break;
-      case 3: keff = qr_pivoted_cached<3>(Y, nv, len, rtol_abs, ncur, nnext, nrmref, rdr, rdi, perm, pcur, pnext, s_cand); break;
-      case 4: keff = qr_pivoted_cached<4>(Y, nv, len, rtol_abs, ncur, nnext, nrmref, rdr, rdi, perm, pcur, pnext, s_cand); break;
-      case 5: keff = qr_pivoted_cached<5>(Y, nv, len, rtol_abs, ncur, nnext, nrmref, rdr, rdi, perm, pcur, pnext, s_cand); break;
-      case 6: keff = qr_pivoted_cached<6>(Y, nv, len, rtol_abs, ncur, nnext, nrmref, rdr, rdi, perm, pcur, pnext, s_cand); break;
-      case 7: keff = qr_pivoted_cached<7>(Y, nv, len, rtol_abs, ncur, nnext, nrmref, rdr, rdi, perm, pcur, pnext, s_cand); break;
-      default: keff = qr_pivoted_cached<8>(Y, nv, len, rtol_abs, ncur, nnext, nrmref, rdr, rdi, perm, pcur, pnext, s_cand); break;
+      case 1: keff = qr_pivoted_cached<1>(q); break;
+      case 2: keff = qr_pivoted_cached<2>(q); break;
+      case 3: keff = qr_pivoted_cached<3>(q); break;
+      case 4: keff = qr_pivoted_cached<4>(q); break;
+      case 5: keff = qr_pivoted_cached<5>(q); break;
+      case 6: keff = qr_pivoted_cached<6>(q); break;
+      case 7: keff = qr_pivoted_cached<7>(q); break;
+      default: keff = qr_pivoted_cached<8>(q); break;
     }
+    ncur = q.ncur; nnext = q.nnext; pcur = q.pcur; pnext = q.pnext;
   }
   if (tid < 3) s_key[tid] = 0ull;
   __syncthreads();
