@@ -127,6 +127,13 @@ struct Workspace {
   cplx* theta = nullptr;
   cplx* cbuf = nullptr;
   DecompBuffers db;
+  // Second set of decomposition buffers + side stream: the block table of decomposition n+1 only depends on bond
+  // labels that are final once decomposition n has truncated, so it is built on `side` while n assembles its factors
+  // (and, before a gate, while the two-site tensor is merged and the gate applied).  Consecutive decompositions of a
+  // Trotter step alternate between db and db2.
+  DecompBuffers db2;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_trunc = nullptr, ev_setup = nullptr;
   // overlaps
   cplx* E[2] = {nullptr, nullptr};
   cplx* T = nullptr;
@@ -218,6 +225,19 @@ int alloc_ws(ocmps_ctx* ctx, int L, int D, int cap, bool with_work, Workspace** 
   CK(cudaMalloc(&w->d_norm, sizeof(double) * 4));
   CK(cudaMalloc(&w->d_params, sizeof(StepParams)));
   w->db.status = ctx->d_status;
+  w->db2 = w->db;                                     // shares status, partial; everything a decomposition writes is separate
+  CK(cudaMalloc(&w->db2.dw, sizeof(DecompWork)));
+  CK(cudaMalloc(&w->db2.vec_idx, sizeof(int) * 3 * NV_MAX));
+  CK(cudaMalloc(&w->db2.comp_idx, sizeof(int) * 3 * NV_MAX));
+  CK(cudaMalloc(&w->db2.vecq, sizeof(int) * NV_MAX));
+  CK(cudaMalloc(&w->db2.P, sizeof(double) * NV_MAX));
+  CK(cudaMalloc(&w->db2.pos, sizeof(int) * 3 * NV_MAX));
+  CK(cudaMalloc(&w->db2.ywork, sizeof(cplx) * 2 * ywhalf));
+  CK(cudaMalloc(&w->db2.scratch_d, sizeof(double) * 8 * NV_MAX));
+  CK(cudaMalloc(&w->db2.descs, sizeof(GemmDesc) * 4));
+  CK(cudaStreamCreateWithFlags(&w->side, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&w->ev_trunc, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&w->ev_setup, cudaEventDisableTiming));
   if (with_work) {
     int rc = alloc_mps(ctx, L, D, cap, &w->work);
     if (rc) return rc;
@@ -245,6 +265,11 @@ void free_ws(Workspace* w) {
   cudaFree(w->theta); cudaFree(w->cbuf); cudaFree(w->db.dw); cudaFree(w->db.vec_idx); cudaFree(w->db.comp_idx);
   cudaFree(w->db.vecq); cudaFree(w->db.P); cudaFree(w->db.pos); cudaFree(w->db.ywork); cudaFree(w->db.descs);
   cudaFree(w->db.partial); cudaFree(w->d_norm); cudaFree(w->db.scratch_d); cudaFree(w->d_params);
+  cudaFree(w->db2.dw); cudaFree(w->db2.vec_idx); cudaFree(w->db2.comp_idx); cudaFree(w->db2.vecq); cudaFree(w->db2.P);
+  cudaFree(w->db2.pos); cudaFree(w->db2.ywork); cudaFree(w->db2.scratch_d); cudaFree(w->db2.descs);
+  if (w->side) cudaStreamDestroy(w->side);
+  if (w->ev_trunc) cudaEventDestroy(w->ev_trunc);
+  if (w->ev_setup) cudaEventDestroy(w->ev_setup);
   for (auto& kv : w->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   free_mps(w->psiH);
   cudaFree(w->E[0]); cudaFree(w->E[1]); cudaFree(w->T); cudaFree(w->odescs); cudaFree(w->d_out);
@@ -392,8 +417,13 @@ std::vector<Op> build_schedule(int L) {
 // decomposition driver
 // ------------------------------------------------------------------------------------------------
 // setup -> QR + Jacobi per charge block -> global truncation -> assembly of isometry and centre factor
-void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int capV, int capC, int capK, cudaStream_t s) {
-  launch_decomp_setup(a, ws->db, s);
+// `db`: buffer set to use; `setup_done`: the block table was already built on the side stream (the caller has made `s`
+// wait for it); `next`: if given, the setup of the following decomposition (buffer set `db_next`) is started on the
+// side stream as soon as this one has truncated.
+void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int capV, int capC, int capK, cudaStream_t s,
+                DecompBuffers* dbp = nullptr, bool setup_done = false, const DecompArgs* next = nullptr, DecompBuffers* db_next = nullptr) {
+  DecompBuffers& db = dbp ? *dbp : ws->db;
+  if (!setup_done) launch_decomp_setup(a, db, s);
   // shared memory: the largest block has at most capV vectors of at most capC components
   size_t need = (size_t)capV * capC * sizeof(cplx);
   // the Jacobi working set stores its rows (<= min(capV, capC) of them) with a stride padded to a multiple of 16
@@ -408,9 +438,15 @@ void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int c
   double rank_tol = 1e-6 * tp.cutoff;
   rank_tol = std::min(1e-14, std::max(1e-30, rank_tol));
   const bool long_rows = capV > 128;                   // rows of R longer than the register-cached path handles
-  launch_jacobi_blocks(a, ws->db, nblk, smem, need_global, long_rows, rank_tol, s);
-  launch_truncate(a, ws->db, tp, s);
-  launch_build_factors(a, ws->db, capK, capV, capC, s);
+  launch_jacobi_blocks(a, db, nblk, smem, need_global, long_rows, rank_tol, s);
+  launch_truncate(a, db, tp, s);
+  if (next) {
+    cudaEventRecord(ws->ev_trunc, s);
+    cudaStreamWaitEvent(ws->side, ws->ev_trunc, 0);
+    launch_decomp_setup(*next, *db_next, ws->side);
+    cudaEventRecord(ws->ev_setup, ws->side);
+  }
+  launch_build_factors(a, db, capK, capV, capC, s);
   g_ocmps_launches += 5 + (need_global ? 1 : 0) + (long_rows ? 1 : 0);
 }
 
@@ -429,6 +465,43 @@ void run_step_body(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, cudaStream_t 
   const StepParams* sp = ws->d_params;
   TruncParams tpg{st->cutoff, st->maxm, 1, st->rel_cutoff, 0, 1};
   TruncParams tpo{MIN_CUT, MAX_M, 1, 0, 0, 0};
+
+  // what decomp_setup_kernel reads of a decomposition op: kind and the labels of the two outer bonds
+  auto setup_args = [&](const Op& op) {
+    DecompArgs a;
+    a.D = D;
+    if (op.kind == 1) {
+      const int bl = op.a - 1, br = op.a + 1;
+      a.kind = op.c == 0 ? DK_GATE_LEFT : DK_GATE_RIGHT;
+      a.dimL = m->dim(bl); a.dimR = m->dim(br); a.qL = m->q(bl); a.qR = m->q(br);
+    } else {
+      const int b = op.a;
+      a.kind = op.b == 0 ? DK_ORTH_LEFT : DK_ORTH_RIGHT;
+      const int lo = op.b == 0 ? b - 1 : b;
+      a.dimL = m->dim(lo); a.dimR = m->dim(lo + 1); a.qL = m->q(lo); a.qR = m->q(lo + 1);
+    }
+    a.dimNew = nullptr; a.qNew = nullptr; a.X = nullptr; a.iso = nullptr; a.partner = nullptr;
+    a.nb_in = nullptr; a.nb_out = nullptr; a.dimNb = nullptr;
+    return a;
+  };
+  const int op_last = std::min((int)st->ops.size(), op_end);
+  int ndec = 0;                    // decompositions issued so far: number n uses buffer set n & 1
+  bool pre_setup = false;          // the setup of the next decomposition is already running on the side stream
+  // issues decomposition `a` of op `oi`; looks ahead for the next decomposition op to start its setup early
+  auto pipelined_decomp = [&](int oi, const DecompArgs& a, const TruncParams& tp, int capV, int capC, int capK) {
+    DecompBuffers* dbc = (ndec & 1) ? &ws->db2 : &ws->db;
+    DecompBuffers* dbn = (ndec & 1) ? &ws->db : &ws->db2;
+    if (pre_setup) cudaStreamWaitEvent(s, ws->ev_setup, 0);
+    int on = oi + 1;
+    while (on < op_last && st->ops[on].kind != 1 && st->ops[on].kind != 2) ++on;
+    DecompArgs an;
+    const bool has_next = on < op_last;
+    if (has_next) an = setup_args(st->ops[on]);
+    run_decomp(ws, a, tp, capV, capC, capK, s, dbc, pre_setup, has_next ? &an : nullptr, dbn);
+    pre_setup = has_next;
+    ++ndec;
+    return dbc;
+  };
 
   for (int oi = op_begin; oi < (int)st->ops.size() && oi < op_end; ++oi) {
     const Op& op = st->ops[oi];
@@ -458,7 +531,7 @@ void run_step_body(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, cudaStream_t 
       const int capV = op.c == 0 ? lay.capb[br] : lay.capb[bl];
       const int capC = op.c == 0 ? lay.capb[bl] : lay.capb[br];
       (void)n_cap; (void)m_cap;
-      run_decomp(ws, a, tpg, capV, capC, lay.capb[bm], s);    // includes the normalisation of :183-184,195-196
+      pipelined_decomp(oi, a, tpg, capV, capC, lay.capb[bm]);  // includes the normalisation of :183-184,195-196
       m->cur[j1] ^= 1; m->cur[j2] ^= 1;
       g_ocmps_launches += 3;
     } else if (op.kind == 2) {
@@ -474,8 +547,8 @@ void run_step_body(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, cudaStream_t 
         a.dimL = m->dim(b - 1); a.dimR = m->dim(b); a.qL = m->q(b - 1); a.qR = m->q(b);
         a.X = m->site(j); a.iso = m->other(j);
         a.nb_in = m->site(jn); a.nb_out = m->other(jn); a.dimNb = m->dim(b + 1);
-        run_decomp(ws, a, tpo, lay.capb[b], lay.capb[b - 1], lay.capb[b], s);
-        launch_zgemm(ws->db.descs + 1, 1, lay.capb[b], D * lay.capb[b + 1], s);
+        DecompBuffers* dbc = pipelined_decomp(oi, a, tpo, lay.capb[b], lay.capb[b - 1], lay.capb[b]);
+        launch_zgemm(dbc->descs + 1, 1, lay.capb[b], D * lay.capb[b + 1], s);
         m->cur[j] ^= 1; m->cur[jn] ^= 1;
       } else {                    // right: SVD of site b+1 (0-based b), U.S pushed into site b
         const int j = b, jn = b - 1;
@@ -483,8 +556,8 @@ void run_step_body(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, cudaStream_t 
         a.dimL = m->dim(b); a.dimR = m->dim(b + 1); a.qL = m->q(b); a.qR = m->q(b + 1);
         a.X = m->site(j); a.iso = m->other(j);
         a.nb_in = m->site(jn); a.nb_out = m->other(jn); a.dimNb = m->dim(b - 1);
-        run_decomp(ws, a, tpo, lay.capb[b], lay.capb[b + 1], lay.capb[b], s);
-        launch_zgemm(ws->db.descs + 1, 1, lay.capb[b - 1] * D, lay.capb[b], s);
+        DecompBuffers* dbc = pipelined_decomp(oi, a, tpo, lay.capb[b], lay.capb[b + 1], lay.capb[b]);
+        launch_zgemm(dbc->descs + 1, 1, lay.capb[b - 1] * D, lay.capb[b], s);
         m->cur[j] ^= 1; m->cur[jn] ^= 1;
       }
       g_ocmps_launches += 1;
