@@ -1156,7 +1156,7 @@ __global__ void __launch_bounds__(1024) truncate_kernel(DecompArgs a, DecompBuff
 //   isometry  u_j = M z_j^H / |M z_j^H|  (scattered into column / row j, zero outside the charge block)
 //   partner   sigma_j z_j * scale         (the tensor that carries the orthogonality centre)
 // ------------------------------------------------------------------------------------------------
-constexpr int BUILD_THREADS = 256;
+constexpr int BUILD_THREADS = 512;
 __global__ void __launch_bounds__(BUILD_THREADS) build_factors_kernel(DecompArgs a, DecompBuffers b) {
   extern __shared__ __align__(16) unsigned char bsm[];
   __shared__ double red[BUILD_THREADS / 32];
@@ -1173,42 +1173,65 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_factors_kernel(DecompArgs
   const int bi = b.pos[NV_MAX + kk], j = b.pos[2 * NV_MAX + kk];
   const DecompBlock B = w->blk[bi];
   const int nv = B.nv, len = B.len;
-  const int* vidx = b.vec_idx + B.vec_off;
-  const int* cidx = b.comp_idx + B.comp_off;
   const cplx* Zj = b.ywork + B.ws_off + (size_t)j * nv;
   const double sigma = sqrt(b.P[B.p_off + j]) * w->scale;
   cplx* zs = reinterpret_cast<cplx*>(bsm);            // z_j (nv)
   cplx* out = zs + nv;                                // M z_j^H (len)
-  const int tid = threadIdx.x;
-  for (int v = tid; v < nv; v += BUILD_THREADS) zs[v] = Zj[v];
+  int* vidx = reinterpret_cast<int*>(out + len);      // index lists of the block, staged: the loads of X below then
+  int* cidx = vidx + nv;                              // depend on nothing but shared memory and can all be in flight
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  constexpr int NW = BUILD_THREADS / 32;
+  for (int v = tid; v < nv; v += BUILD_THREADS) { zs[v] = Zj[v]; vidx[v] = b.vec_idx[B.vec_off + v]; }
+  for (int c = tid; c < len; c += BUILD_THREADS) cidx[c] = b.comp_idx[B.comp_off + c];
   __syncthreads();
   double part = 0.0;
   if (mode == 0) {
-    // vectors are columns of X: one warp per output component, lanes stride over the (nearly contiguous) columns
-    const int lane = tid & 31, wp = tid >> 5;
-    for (int c = wp; c < len; c += BUILD_THREADS / 32) {
+    // vectors are columns of X: one warp per output component, lanes stride over the (nearly contiguous) columns,
+    // four independent loads per lane and pass
+    for (int c = wp; c < len; c += NW) {
       const cplx* row = a.X + (size_t)cidx[c] * ld;
       double sr = 0.0, si = 0.0;
-      for (int v = lane; v < nv; v += 32) {
-        const cplx x = row[vidx[v]], z = zs[v];
-        sr += x.x * z.x + x.y * z.y;          // x * conj(z)
-        si += x.y * z.x - x.x * z.y;
+      for (int v0 = 0; v0 < nv; v0 += 128) {
+        cplx x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int v = v0 + lane + 32 * u;
+          x[u] = make_double2(0.0, 0.0);
+          if (v < nv) x[u] = row[vidx[v]];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int v = v0 + lane + 32 * u;
+          if (v < nv) {
+            const cplx z = zs[v];
+            sr += x[u].x * z.x + x[u].y * z.y;          // x * conj(z)
+            si += x[u].y * z.x - x[u].x * z.y;
+          }
+        }
       }
       sr = warp_sum(sr); si = warp_sum(si);
       if (lane == 0) { out[c] = make_double2(sr, si); part += sr * sr + si * si; }
     }
   } else {
-    // vectors are rows of X: one thread per output component, consecutive threads read consecutive columns
-    for (int c = tid; c < len; c += BUILD_THREADS) {
-      const int col = cidx[c];
+    // vectors are rows of X: a warp takes 8 consecutive output components x 4 interleaved ranges of vectors
+    // (consecutive lanes read consecutive columns), reduced over the ranges with two shuffles
+    const int cl = lane & 7, g = lane >> 3;
+    for (int c0 = 8 * wp; c0 < len; c0 += 8 * NW) {
+      const int c = c0 + cl;
+      const bool in = c < len;
+      const cplx* colp = a.X + (in ? cidx[c] : 0);
       double sr = 0.0, si = 0.0;
-      for (int v = 0; v < nv; ++v) {
-        const cplx x = a.X[(size_t)vidx[v] * ld + col], z = zs[v];
-        sr += x.x * z.x + x.y * z.y;
-        si += x.y * z.x - x.x * z.y;
+      if (in) {
+#pragma unroll 4
+        for (int v = g; v < nv; v += 4) {
+          const cplx x = colp[(size_t)vidx[v] * ld], z = zs[v];
+          sr += x.x * z.x + x.y * z.y;
+          si += x.y * z.x - x.x * z.y;
+        }
       }
-      out[c] = make_double2(sr, si);
-      part += sr * sr + si * si;
+      sr += __shfl_xor_sync(0xffffffffu, sr, 8);  si += __shfl_xor_sync(0xffffffffu, si, 8);
+      sr += __shfl_xor_sync(0xffffffffu, sr, 16); si += __shfl_xor_sync(0xffffffffu, si, 16);
+      if (in && g == 0) { out[c] = make_double2(sr, si); part += sr * sr + si * si; }
     }
   }
   part = warp_sum(part);
@@ -1345,7 +1368,7 @@ void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_
   if (dev < 64 && !g_jac_attr_set[dev]) {
     cudaFuncSetAttribute(jacobi_blocks_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(jacobi_blocks_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(build_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(build_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cudaFuncSetAttribute(jacobi_rot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(JAC_BLOCKED_ROWS * 16 * JAC_EPL * sizeof(cplx)));
     g_jac_attr_set[dev] = true;
   }
@@ -1361,7 +1384,7 @@ void launch_truncate(const DecompArgs& a, const DecompBuffers& b, const TruncPar
 }
 
 void launch_build_factors(const DecompArgs& a, const DecompBuffers& b, int cap_k, int cap_vec, int cap_comp, cudaStream_t s) {
-  const size_t sm = sizeof(cplx) * (size_t)(cap_vec + cap_comp);
+  const size_t sm = (sizeof(cplx) + sizeof(int)) * (size_t)(cap_vec + cap_comp);
   build_factors_kernel<<<cap_k, BUILD_THREADS, sm, s>>>(a, b);
 }
 
