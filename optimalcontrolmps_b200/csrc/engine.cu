@@ -435,8 +435,9 @@ void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int c
   int nblk = std::min(std::min(OCMPS_MAX_BLK, std::max(capV, capC) + a.D), ws->ctx->qmax + a.D + 1);
   const bool need_global = need > JAC_SMEM_LIMIT;    // some block may not fit in shared memory
   // numerical-rank tolerance of the pivoted QR: the neglected weight stays >= 6 orders below the cutoff
-  double rank_tol = 1e-6 * tp.cutoff;
-  rank_tol = std::min(1e-14, std::max(1e-30, rank_tol));
+  static const double rank_scale = [] { const char* e = getenv("OCMPS_RANK_TOL_SCALE"); return e ? atof(e) : 1e-6; }();
+  double rank_tol = rank_scale * tp.cutoff;
+  rank_tol = std::min(rank_scale * 1e-8, std::max(1e-30, rank_tol));
   const bool long_rows = capV > 128;                   // rows of R longer than the register-cached path handles
   launch_jacobi_blocks(a, db, nblk, smem, need_global, long_rows, rank_tol, s);
   launch_truncate(a, db, tp, s);
