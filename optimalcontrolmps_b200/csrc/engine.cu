@@ -513,10 +513,17 @@ void run_step_body(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, cudaStream_t 
     } else if (op.kind == 1) {
       const int j1 = op.a - 1, j2 = op.a;                 // 0-based sites
       const int bl = j1, bm = j1 + 1, br = j2 + 1;        // bonds
-      launch_merge_setup(ws->db.descs + 2, m->site(j1), m->site(j2), ws->theta, m->dim(bl), m->dim(bm), m->dim(br), D, s);
-      launch_zgemm(ws->db.descs + 2, 1, lay.capb[bl] * D, D * lay.capb[br], s);
       // op.b: 0 = U(from) then J (:150), 1 = plus the lonely U(to) on the last site (:153-155), 2 = J then U(to) (:159)
-      launch_gate_apply(ws->theta, m->dim(bl), m->dim(br), m->q(bl), m->q(br), D, sp, op.b, lay.capb[bl], lay.capb[br], s);
+      static const bool fused_merge = [] { const char* e = getenv("OCMPS_FUSED_MERGE"); return !(e && e[0] == '0'); }();
+      if (fused_merge && D >= 2 && D <= 8) {
+        launch_merge_gate(m->site(j1), m->site(j2), ws->theta, m->dim(bl), m->dim(bm), m->dim(br), m->q(bl), m->q(bm), m->q(br), D, sp,
+                          op.b, lay.capb[bl], lay.capb[br], s);
+        g_ocmps_launches -= 2;
+      } else {
+        launch_merge_setup(ws->db.descs + 2, m->site(j1), m->site(j2), ws->theta, m->dim(bl), m->dim(bm), m->dim(br), D, s);
+        launch_zgemm(ws->db.descs + 2, 1, lay.capb[bl] * D, D * lay.capb[br], s);
+        launch_gate_apply(ws->theta, m->dim(bl), m->dim(br), m->q(bl), m->q(br), D, sp, op.b, lay.capb[bl], lay.capb[br], s);
+      }
       DecompArgs a;
       a.kind = op.c == 0 ? DK_GATE_LEFT : DK_GATE_RIGHT;
       a.D = D;

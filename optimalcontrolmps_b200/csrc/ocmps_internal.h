@@ -123,6 +123,9 @@ void launch_build_factors(const DecompArgs& a, const DecompBuffers& b, int cap_k
 void launch_merge_setup(GemmDesc* d, const cplx* A1, const cplx* A2, cplx* theta, const int* dimL, const int* dimM,
                         const int* dimR, int D, cudaStream_t s);
 // gate_kind: 0 = U(from) then J, 1 = same plus the lonely U(to) on the second site, 2 = J then U(to)
+void launch_merge_gate(const cplx* A1, const cplx* A2, cplx* theta, const int* dimL, const int* dimM, const int* dimR,
+                       const int* qL, const int* qM, const int* qR, int D, const StepParams* sp, int gate_kind, int maxL, int maxR,
+                       cudaStream_t s);
 void launch_gate_apply(cplx* theta, const int* dimL, const int* dimR, const int* qL, const int* qR, int D, const StepParams* sp,
                        int gate_kind, int maxL, int maxR, cudaStream_t s);
 void launch_site_phase(cplx* A, const int* dimL, const int* dimR, int D, const StepParams* sp, int which, int max_elems, cudaStream_t s);
