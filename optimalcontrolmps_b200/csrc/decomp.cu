@@ -1251,6 +1251,46 @@ __global__ void __launch_bounds__(BUILD_THREADS) build_factors_kernel(DecompArgs
     if (comp_blk[c] == bi) { const cplx o = out[comp_rank[c]]; v = make_double2(o.x * inv, o.y * inv); }
     if (mode == 0) a.iso[(size_t)c * k + kk] = v; else a.iso[(size_t)kk * m + c] = v;
   }
+  if (a.qNb != nullptr && (a.kind == DK_ORTH_LEFT || a.kind == DK_ORTH_RIGHT)) {
+    // gauge push fused in: row / column kk of (carry matrix . neighbour).  The carry sigma_j z_j lives in one charge
+    // sector, so for every far-bond index exactly one physical index of the neighbour contributes.
+    const int D = a.D, chiFar = *a.dimNb, qj = B.q;
+    if (a.kind == DK_ORTH_LEFT) {        // out[kk][s][r] = sum_v C[kk][v] nb[v][s][r],  s = qFar[r] - q_j
+      const long long far = (long long)D * chiFar;
+      for (int r = tid; r < chiFar; r += BUILD_THREADS) {
+        const int sx = a.qNb[r] - qj;
+        double ar = 0.0, ai = 0.0;
+        if (sx >= 0 && sx < D) {
+          const cplx* col = a.nb_in + (long long)sx * chiFar + r;
+#pragma unroll 4
+          for (int t = 0; t < nv; ++t) {
+            const cplx z = zs[t], x = col[(long long)vidx[t] * far];
+            ar += z.x * x.x - z.y * x.y;
+            ai += z.x * x.y + z.y * x.x;
+          }
+        }
+        for (int sp = 0; sp < D; ++sp)
+          a.nb_out[(long long)kk * far + (long long)sp * chiFar + r] = sp == sx ? make_double2(ar * sigma, ai * sigma) : make_double2(0.0, 0.0);
+      }
+    } else {                             // out[l][s][kk] = sum_v nb[l][s][v] C[v][kk],  s = q_j - qFar[l]
+      for (int l = tid; l < chiFar; l += BUILD_THREADS) {
+        const int sx = qj - a.qNb[l];
+        double ar = 0.0, ai = 0.0;
+        if (sx >= 0 && sx < D) {
+          const cplx* row = a.nb_in + ((long long)l * D + sx) * n;
+#pragma unroll 4
+          for (int t = 0; t < nv; ++t) {
+            const cplx z = zs[t], x = row[vidx[t]];
+            ar += z.x * x.x - z.y * x.y;
+            ai += z.x * x.y + z.y * x.x;
+          }
+        }
+        for (int sp = 0; sp < D; ++sp)
+          a.nb_out[((long long)l * D + sp) * k + kk] = sp == sx ? make_double2(ar * sigma, ai * sigma) : make_double2(0.0, 0.0);
+      }
+    }
+    return;
+  }
   for (int v = tid; v < nvec; v += BUILD_THREADS) {
     cplx o = make_double2(0.0, 0.0);
     if (vec_blk[v] == bi) { const cplx z = zs[vec_rank[v]]; o = make_double2(z.x * sigma, z.y * sigma); }

@@ -459,6 +459,12 @@ void phases_of(int D, double U, double tstep, double* re, double* im) {
   }
 }
 
+// gauge pushes done inside build_factors (sector-wise) instead of a dense GEMM that follows it; OCMPS_FUSED_PUSH=0 restores the GEMM
+static bool fused_push_enabled() {
+  static const bool v = [] { const char* e = getenv("OCMPS_FUSED_PUSH"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
 // the kernel sequence of one Trotter step in place on `m` (all step-dependent values are read from ws->d_params)
 void run_step_body(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, cudaStream_t s, int op_begin = 0, int op_end = 1 << 30) {
   const int L = st->L, D = st->D;
@@ -482,9 +488,10 @@ void run_step_body(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, cudaStream_t 
       a.dimL = m->dim(lo); a.dimR = m->dim(lo + 1); a.qL = m->q(lo); a.qR = m->q(lo + 1);
     }
     a.dimNew = nullptr; a.qNew = nullptr; a.X = nullptr; a.iso = nullptr; a.partner = nullptr;
-    a.nb_in = nullptr; a.nb_out = nullptr; a.dimNb = nullptr;
+    a.nb_in = nullptr; a.nb_out = nullptr; a.dimNb = nullptr; a.qNb = nullptr;
     return a;
   };
+  const bool fused_push = fused_push_enabled();
   const int op_last = std::min((int)st->ops.size(), op_end);
   int ndec = 0;                    // decompositions issued so far: number n uses buffer set n & 1
   bool pre_setup = false;          // the setup of the next decomposition is already running on the side stream
@@ -532,7 +539,7 @@ void run_step_body(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, cudaStream_t 
       a.X = ws->theta;
       a.iso = op.c == 0 ? m->other(j1) : m->other(j2);
       a.partner = op.c == 0 ? m->other(j2) : m->other(j1);
-      a.nb_in = nullptr; a.nb_out = nullptr; a.dimNb = nullptr;
+      a.nb_in = nullptr; a.nb_out = nullptr; a.dimNb = nullptr; a.qNb = nullptr;
       tpg.cap = lay.capb[bm];
       const int n_cap = lay.capb[bl] * D, m_cap = D * lay.capb[br];
       // vectors per block <= chi of their own side, components <= chi of the other side
@@ -555,8 +562,9 @@ void run_step_body(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, cudaStream_t 
         a.dimL = m->dim(b - 1); a.dimR = m->dim(b); a.qL = m->q(b - 1); a.qR = m->q(b);
         a.X = m->site(j); a.iso = m->other(j);
         a.nb_in = m->site(jn); a.nb_out = m->other(jn); a.dimNb = m->dim(b + 1);
+        a.qNb = fused_push ? m->q(b + 1) : nullptr;
         DecompBuffers* dbc = pipelined_decomp(oi, a, tpo, lay.capb[b], lay.capb[b - 1], lay.capb[b]);
-        launch_zgemm(dbc->descs + 1, 1, lay.capb[b], D * lay.capb[b + 1], s);
+        if (!fused_push) launch_zgemm(dbc->descs + 1, 1, lay.capb[b], D * lay.capb[b + 1], s);
         m->cur[j] ^= 1; m->cur[jn] ^= 1;
       } else {                    // right: SVD of site b+1 (0-based b), U.S pushed into site b
         const int j = b, jn = b - 1;
@@ -564,11 +572,12 @@ void run_step_body(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, cudaStream_t 
         a.dimL = m->dim(b); a.dimR = m->dim(b + 1); a.qL = m->q(b); a.qR = m->q(b + 1);
         a.X = m->site(j); a.iso = m->other(j);
         a.nb_in = m->site(jn); a.nb_out = m->other(jn); a.dimNb = m->dim(b - 1);
+        a.qNb = fused_push ? m->q(b - 1) : nullptr;
         DecompBuffers* dbc = pipelined_decomp(oi, a, tpo, lay.capb[b], lay.capb[b + 1], lay.capb[b]);
-        launch_zgemm(dbc->descs + 1, 1, lay.capb[b - 1] * D, lay.capb[b], s);
+        if (!fused_push) launch_zgemm(dbc->descs + 1, 1, lay.capb[b - 1] * D, lay.capb[b], s);
         m->cur[j] ^= 1; m->cur[jn] ^= 1;
       }
-      g_ocmps_launches += 1;
+      g_ocmps_launches += fused_push ? 0 : 1;
     } else {
       const int j = op.a - 1;
       launch_normalize_site(m->site(j), m->dim(j), m->dim(j + 1), D, ws->db.partial, lay.capb[j] * D * lay.capb[j + 1], s);
@@ -784,9 +793,10 @@ int apply_K_async(ocmps_stepper* st, Workspace* ws, ocmps_mps* in, ocmps_mps* ou
     a.dimL = big->dim(b - 1); a.dimR = big->dim(b); a.qL = big->q(b - 1); a.qR = big->q(b);
     a.X = big->site(j); a.iso = big->other(j);
     a.nb_in = big->site(jn); a.nb_out = big->other(jn); a.dimNb = big->dim(b + 1);
+    a.qNb = fused_push_enabled() ? big->q(b + 1) : nullptr;
     tpl.cap = lb.capb[b];
     run_decomp(bw, a, tpl, lb.capb[b], lb.capb[b - 1], lb.capb[b], s);
-    launch_zgemm(bw->db.descs + 1, 1, lb.capb[b], D * lb.capb[b + 1], s);
+    if (!a.qNb) launch_zgemm(bw->db.descs + 1, 1, lb.capb[b], D * lb.capb[b + 1], s);
     big->cur[j] ^= 1; big->cur[jn] ^= 1;
     g_ocmps_launches += 1;
   }
@@ -800,9 +810,10 @@ int apply_K_async(ocmps_stepper* st, Workspace* ws, ocmps_mps* in, ocmps_mps* ou
     a.dimL = big->dim(b); a.dimR = big->dim(b + 1); a.qL = big->q(b); a.qR = big->q(b + 1);
     a.X = big->site(j); a.iso = big->other(j);
     a.nb_in = big->site(jn); a.nb_out = big->other(jn); a.dimNb = big->dim(b - 1);
+    a.qNb = fused_push_enabled() ? big->q(b - 1) : nullptr;
     tpr.cap = std::min(lb.capb[b], out->lay.capb[b]);
     run_decomp(bw, a, tpr, lb.capb[b], lb.capb[b + 1], tpr.cap, s);
-    launch_zgemm(bw->db.descs + 1, 1, lb.capb[b - 1] * D, lb.capb[b], s);
+    if (!a.qNb) launch_zgemm(bw->db.descs + 1, 1, lb.capb[b - 1] * D, lb.capb[b], s);
     big->cur[j] ^= 1; big->cur[jn] ^= 1;
     g_ocmps_launches += 1;
   }

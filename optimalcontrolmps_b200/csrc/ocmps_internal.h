@@ -97,6 +97,8 @@ struct DecompArgs {
   const cplx* nb_in;        // orth kinds: neighbouring site tensor (input)
   cplx* nb_out;             // orth kinds: neighbouring site tensor (output)
   const int* dimNb;         // orth kinds: far bond dimension of the neighbour
+  const int* qNb;           // orth kinds: charges of that far bond; if set, build_factors pushes the carry matrix into
+                            // the neighbour itself (sector by sector) and no GEMM follows; nullptr: caller runs descs[1]
 };
 
 struct DecompBuffers {
