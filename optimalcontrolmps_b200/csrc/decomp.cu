@@ -954,7 +954,7 @@ __global__ void __launch_bounds__(1024) truncate_kernel(DecompArgs a, DecompBuff
   // compacted first, so the two O(n^2 / threads) ranking loops run over the candidates only.
   __shared__ double cP[NV_MAX];           // candidate weights, compact
   __shared__ double sSorted[NV_MAX];      // descending; then overwritten by its suffix sums
-  __shared__ short cQ[NV_MAX], cI[NV_MAX];
+  __shared__ short cQ[NV_MAX], cI[NV_MAX], cI2[NV_MAX];   // charge, original index, kept candidates before
   __shared__ unsigned char sKeep[NV_MAX];
   __shared__ int sBlkOff[OCMPS_MAX_BLK + 1];
   __shared__ double sWarp[32];
@@ -991,15 +991,24 @@ __global__ void __launch_bounds__(1024) truncate_kernel(DecompArgs a, DecompBuff
     if (f1) { cP[k] = p1; cQ[k] = (short)b.vecq[i1]; cI[k] = (short)i1; }
   }
   __syncthreads();
-  // ---- descending rank of every candidate ----
-  for (int k = tid; k < nnz; k += blockDim.x) {
-    const double pk = cP[k];
-    int rank = 0;
-    for (int j = 0; j < nnz; ++j) {
-      const double pj = cP[j];
-      rank += (pj > pk) || (pj == pk && j < k);
+  // ---- descending rank of every candidate: tpe (1..8) threads share the comparisons of one candidate ----
+  {
+    int tpe = 1;
+    while (tpe < 8 && nnz * tpe * 2 <= (int)blockDim.x) tpe *= 2;
+    const int sub = tid & (tpe - 1);
+    for (int k0 = 0; k0 < nnz; k0 += (int)blockDim.x / tpe) {        // uniform trip count (shuffles inside)
+      const int k = k0 + tid / tpe;
+      const bool in = k < nnz;
+      const double pk = in ? cP[k] : 0.0;
+      int rank = 0;
+      if (in)
+        for (int j = sub; j < nnz; j += tpe) {
+          const double pj = cP[j];
+          rank += (pj > pk) || (pj == pk && j < k);
+        }
+      for (int o = 1; o < tpe; o <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+      if (in && sub == 0) sSorted[rank] = pk;
     }
-    sSorted[rank] = pk;
   }
   __syncthreads();
   // ---- suffix sums Suf[n] = sum_{i >= n} sorted[i] (ITensor accumulates them in `truncerr` walking up from the small
@@ -1068,13 +1077,33 @@ __global__ void __launch_bounds__(1024) truncate_kernel(DecompArgs a, DecompBuff
     __syncthreads();
   }
   const double docut = s_docut;
-  for (int k = tid; k < nnz; k += blockDim.x) {
-    const unsigned char kp = cP[k] > docut;
-    sKeep[k] = kp;
-    if (kp) atomicAdd(&s_total, 1);
+  // ---- kept flags and their running count.  Candidates are in block order and blocks in ascending charge order, so
+  // the new index of a kept state = kept states before its charge run + its rank by weight inside the run ----
+  {
+    const int ka = 2 * tid, kb = ka + 1;
+    const int fa = ka < nnz && cP[ka] > docut, fb = kb < nnz && cP[kb] > docut;
+    if (ka < nnz) sKeep[ka] = (unsigned char)fa;
+    if (kb < nnz) sKeep[kb] = (unsigned char)fb;
+    int inc = fa + fb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int up = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += up; }
+    __syncthreads();                   // (sWarpCnt is free again)
+    if (lane == 31) sWarpCnt[warp + 1] = inc;
+    if (tid == 0) sWarpCnt[0] = 0;
+    __syncthreads();
+    if (warp == 0) {
+      int v = sWarpCnt[lane + 1];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int up = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += up; }
+      sWarpCnt[lane + 1] = v;
+    }
+    __syncthreads();
+    const int base = sWarpCnt[warp] + inc - fa - fb;     // kept candidates before ka
+    if (ka < nnz) cI2[ka] = (short)base;
+    if (kb < nnz) cI2[kb] = (short)(base + fa);
   }
   __syncthreads();
-  const int total = s_total;
+  const int total = sWarpCnt[32];
   int* inv_blk = b.pos + NV_MAX;       // per new index: block id, vector-in-block
   int* inv_v = b.pos + 2 * NV_MAX;
   double part = 0.0;
@@ -1082,13 +1111,11 @@ __global__ void __launch_bounds__(1024) truncate_kernel(DecompArgs a, DecompBuff
     if (!sKeep[k]) continue;
     const int qk = cQ[k];
     const double pk = cP[k];
-    int pos = 0;
-    for (int j = 0; j < nnz; ++j) {
-      if (!sKeep[j]) continue;
-      const int qj = cQ[j];
-      const double pj = cP[j];
-      pos += (qj < qk) || (qj == qk && (pj > pk || (pj == pk && j < k)));
-    }
+    int rank = 0, j = k - 1;
+    for (; j >= 0 && cQ[j] == qk; --j) rank += sKeep[j] && cP[j] >= pk;        // ties: the earlier candidate first
+    const int pos0 = cI2[j + 1];                                              // kept before the run of this charge
+    for (j = k + 1; j < nnz && cQ[j] == qk; ++j) rank += sKeep[j] && cP[j] > pk;
+    const int pos = pos0 + rank;
     if (pos < tp.cap) {
       const int i = cI[k];
       a.qNew[pos] = qk;
