@@ -93,17 +93,16 @@ __global__ void __launch_bounds__(128) gate_apply_kernel(cplx* __restrict__ thet
 //   theta'[l,t1,t2,r] = sum_{s1+s2=N} W[(t1,t2),(s1,s2)] sum_{mid: q(mid) = qL[l]+s1} A1[l,s1,mid] A2[mid,s2,r],   N = qR[r] - qL[l]
 // Only the charge-allowed entries of theta are computed and written (the decomposition that follows gathers exactly
 // those); as a dense GEMM the merge would spend ~98 % of its multiply-adds on structural zeros.  The middle bond is
-// sorted by charge, so the mids of one sector are a contiguous range.  One thread per (l, r), a warp shares l: the
-// A1 loads are broadcasts, the A2 loads are coalesced over r.
+// sorted by charge, so the mids of one sector are a contiguous range.  Four lanes per (l, r), each taking every fourth
+// mid (the kernel is a chain of L2 latencies, so the loop is kept short and many loads are in flight); a warp shares l:
+// the A1 loads are broadcasts, the A2 loads are coalesced over 8 consecutive r.
 template <int D>
 __global__ void __launch_bounds__(128) merge_gate_kernel(const cplx* __restrict__ A1, const cplx* __restrict__ A2, cplx* __restrict__ theta,
                                                         const int* dimL, const int* dimM, const int* dimR,
                                                         const int* __restrict__ qL, const int* __restrict__ qM, const int* __restrict__ qR,
                                                         const StepParams* __restrict__ sp, int gate_kind) {
-  extern __shared__ __align__(16) unsigned char gate_smem[];
   __shared__ Phases ph;
   __shared__ int s_start[OCMPS_MAX_Q + 2];           // first mid whose charge is >= c
-  cplx* W = reinterpret_cast<cplx*>(gate_smem);
   const int chiL = *dimL, chiM = *dimM, chiR = *dimR;
   const cplx* __restrict__ G = sp->G;
   if (threadIdx.x < D) {                       // [0],[1]: phases before the J gate on site 1, 2; [2],[3]: after it
@@ -121,18 +120,8 @@ __global__ void __launch_bounds__(128) merge_gate_kernel(const cplx* __restrict_
     for (int c = lo; c <= hi; ++c) s_start[c] = i;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < D * D * D * D; e += blockDim.x) {
-    const int row = e / (D * D), col = e % (D * D);
-    const int t1 = row / D, t2 = row % D, s1 = col / D, s2 = col % D;
-    double fr = ph.re[0][s1], fi = ph.im[0][s1];
-    double xr = fr * ph.re[1][s2] - fi * ph.im[1][s2], xi = fr * ph.im[1][s2] + fi * ph.re[1][s2];
-    fr = xr * ph.re[2][t1] - xi * ph.im[2][t1]; fi = xr * ph.im[2][t1] + xi * ph.re[2][t1];
-    xr = fr * ph.re[3][t2] - fi * ph.im[3][t2]; xi = fr * ph.im[3][t2] + fi * ph.re[3][t2];
-    const cplx g = G[e];
-    W[e] = make_double2(g.x * xr - g.y * xi, g.x * xi + g.y * xr);
-  }
-  __syncthreads();
-  const int r = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane = threadIdx.x & 31, g = lane >> 3;
+  const int r = blockIdx.x * 8 + (lane & 7);
   const int l = blockIdx.y * 4 + (threadIdx.x >> 5);
   if (l >= chiL) return;                                   // (warp uniform)
   const bool rin = r < chiR;
@@ -152,33 +141,41 @@ __global__ void __launch_bounds__(128) merge_gate_kernel(const cplx* __restrict_
     const cplx* a2 = A2 + (act ? (long long)s2 * chiR + r : 0);
     double ar = 0.0, ai = 0.0;
 #pragma unroll 4
-    for (int mid = m0; mid < m1; ++mid) {
+    for (int mid = m0 + g; mid < m1; mid += 4) {
       const cplx x = a1[mid];
       cplx y = make_double2(0.0, 0.0);
       if (act) y = a2[(long long)mid * rowstride];
       ar += x.x * y.x - x.y * y.y;
       ai += x.x * y.y + x.y * y.x;
     }
-    in[s1] = make_double2(ar, ai);
+    ar += __shfl_xor_sync(0xffffffffu, ar, 8);  ai += __shfl_xor_sync(0xffffffffu, ai, 8);
+    ar += __shfl_xor_sync(0xffffffffu, ar, 16); ai += __shfl_xor_sync(0xffffffffu, ai, 16);
+    if (act) {                                             // on-site phases before the hopping gate
+      const double fr = ph.re[0][s1] * ph.re[1][s2] - ph.im[0][s1] * ph.im[1][s2];
+      const double fi = ph.re[0][s1] * ph.im[1][s2] + ph.im[0][s1] * ph.re[1][s2];
+      in[s1] = make_double2(ar * fr - ai * fi, ar * fi + ai * fr);
+    }
   }
   if (!ok) return;
   cplx* base = theta + (long long)l * D * rowstride + r;
 #pragma unroll
   for (int t1 = 0; t1 < D; ++t1) {
     const int t2 = N - t1;
-    if (t2 < 0 || t2 >= D) continue;
-    const int row = t1 * D + t2;
+    if (t2 < 0 || t2 >= D || (t1 & 3) != g) continue;      // the four lanes of an (l, r) share the outputs
+    const cplx* Grow = G + (t1 * D + t2) * D * D;
     double ar = 0.0, ai = 0.0;
 #pragma unroll
     for (int s1 = 0; s1 < D; ++s1) {
       const int s2 = N - s1;
       if (s2 >= 0 && s2 < D) {
-        const cplx w = W[row * D * D + s1 * D + s2];
+        const cplx w = Grow[s1 * D + s2];
         ar += w.x * in[s1].x - w.y * in[s1].y;
         ai += w.x * in[s1].y + w.y * in[s1].x;
       }
     }
-    base[t1 * rowstride + (long long)t2 * chiR] = make_double2(ar, ai);
+    const double fr = ph.re[2][t1] * ph.re[3][t2] - ph.im[2][t1] * ph.im[3][t2];     // on-site phases after it
+    const double fi = ph.re[2][t1] * ph.im[3][t2] + ph.im[2][t1] * ph.re[3][t2];
+    base[t1 * rowstride + (long long)t2 * chiR] = make_double2(ar * fr - ai * fi, ar * fi + ai * fr);
   }
 }
 
@@ -359,21 +356,15 @@ void launch_gate_apply(cplx* theta, const int* dimL, const int* dimR, const int*
 void launch_merge_gate(const cplx* A1, const cplx* A2, cplx* theta, const int* dimL, const int* dimM, const int* dimR,
                        const int* qL, const int* qM, const int* qR, int D, const StepParams* sp, int gate_kind, int maxL, int maxR,
                        cudaStream_t s) {
-  dim3 grid((maxR + 31) / 32, (maxL + 3) / 4);
-  const size_t sm = sizeof(cplx) * D * D * D * D;
-  static bool attr8 = false;
-  if (D == 8 && !attr8) {
-    cudaFuncSetAttribute(merge_gate_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    attr8 = true;
-  }
+  dim3 grid((maxR + 7) / 8, (maxL + 3) / 4);
   switch (D) {
-    case 2: merge_gate_kernel<2><<<grid, 128, sm, s>>>(A1, A2, theta, dimL, dimM, dimR, qL, qM, qR, sp, gate_kind); break;
-    case 3: merge_gate_kernel<3><<<grid, 128, sm, s>>>(A1, A2, theta, dimL, dimM, dimR, qL, qM, qR, sp, gate_kind); break;
-    case 4: merge_gate_kernel<4><<<grid, 128, sm, s>>>(A1, A2, theta, dimL, dimM, dimR, qL, qM, qR, sp, gate_kind); break;
-    case 5: merge_gate_kernel<5><<<grid, 128, sm, s>>>(A1, A2, theta, dimL, dimM, dimR, qL, qM, qR, sp, gate_kind); break;
-    case 6: merge_gate_kernel<6><<<grid, 128, sm, s>>>(A1, A2, theta, dimL, dimM, dimR, qL, qM, qR, sp, gate_kind); break;
-    case 7: merge_gate_kernel<7><<<grid, 128, sm, s>>>(A1, A2, theta, dimL, dimM, dimR, qL, qM, qR, sp, gate_kind); break;
-    case 8: merge_gate_kernel<8><<<grid, 128, sm, s>>>(A1, A2, theta, dimL, dimM, dimR, qL, qM, qR, sp, gate_kind); break;
+    case 2: merge_gate_kernel<2><<<grid, 128, 0, s>>>(A1, A2, theta, dimL, dimM, dimR, qL, qM, qR, sp, gate_kind); break;
+    case 3: merge_gate_kernel<3><<<grid, 128, 0, s>>>(A1, A2, theta, dimL, dimM, dimR, qL, qM, qR, sp, gate_kind); break;
+    case 4: merge_gate_kernel<4><<<grid, 128, 0, s>>>(A1, A2, theta, dimL, dimM, dimR, qL, qM, qR, sp, gate_kind); break;
+    case 5: merge_gate_kernel<5><<<grid, 128, 0, s>>>(A1, A2, theta, dimL, dimM, dimR, qL, qM, qR, sp, gate_kind); break;
+    case 6: merge_gate_kernel<6><<<grid, 128, 0, s>>>(A1, A2, theta, dimL, dimM, dimR, qL, qM, qR, sp, gate_kind); break;
+    case 7: merge_gate_kernel<7><<<grid, 128, 0, s>>>(A1, A2, theta, dimL, dimM, dimR, qL, qM, qR, sp, gate_kind); break;
+    case 8: merge_gate_kernel<8><<<grid, 128, 0, s>>>(A1, A2, theta, dimL, dimM, dimR, qL, qM, qR, sp, gate_kind); break;
     default: break;
   }
 }
