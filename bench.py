@@ -329,7 +329,7 @@ def run_ours(args):
             except Exception:
                 traffic = None
         ach = fl_blk / (ms_tot * 1e-3) / 1e12 if ms_tot > 0 else 0.0
-        line["roofline"] = {"kernel": "jacobi_blocks_kernel (QR-preconditioned block Jacobi SVD)", "bound": "tensor",
+        line["roofline"] = {"kernel": "jacobi_blocks_kernel + jacobi_rot_kernel (pivoted QR + block Jacobi SVD of every charge block)", "bound": "tensor",
                             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
                             "traffic": traffic, "launches": int(nl), "avg_launch_us": ms_tot * 1e3 / max(nl, 1),
                             "share_of_two_stream_time": ms_tot / (2.0 * t_dev / args.steps * 1e3),

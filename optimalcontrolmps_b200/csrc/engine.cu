@@ -148,6 +148,7 @@ struct Workspace {
   double* d_norm = nullptr;    // scalar outputs
   StepParams* d_params = nullptr;   // per-step scalars and pointers (device), see StepParams
   ocmps_mps* psiH = nullptr;        // Hessian-row state of this chain
+  ocmps_store* rowstore = nullptr;  // Hessian rows: the last few propagated slices, overlapped with xiH in one batched pass
   // CUDA graphs of one Trotter step (+ slice store), keyed by stepper serial, MPS buffers, buffer parity, with/without store
   struct StepGraph { cudaGraphExec_t exec = nullptr; unsigned long long flips = 0; int launches = 0; int seen = 0; };
   std::map<std::tuple<long long, const void*, unsigned long long, int>, StepGraph> graphs;
@@ -272,6 +273,7 @@ void free_ws(Workspace* w) {
   if (w->ev_setup) cudaEventDestroy(w->ev_setup);
   for (auto& kv : w->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   free_mps(w->psiH);
+  if (w->rowstore) { cudaFree(w->rowstore->data); cudaFree(w->rowstore->dims); cudaFree(w->rowstore->q); delete w->rowstore; }
   cudaFree(w->E[0]); cudaFree(w->E[1]); cudaFree(w->T); cudaFree(w->odescs); cudaFree(w->d_out);
   free_mps(w->work); free_mps(w->big);
   if (w->bigws) free_ws(w->bigws);
@@ -1430,6 +1432,24 @@ int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* x
     }
     psiH[c] = wss[c]->psiH;
   }
+  // The overlaps <xiH_j|psiH_j> of a row are not taken step by step (60+ dependent small launches per step): the
+  // propagated slices go to a per-chain store of `chunk` slots and are overlapped with the matching xiH slices in one
+  // batched transfer-matrix pass per chunk.
+  int chunk = 32;
+  if (const char* e = getenv("OCMPS_HESSIAN_CHUNK")) chunk = std::max(1, atoi(e));
+  chunk = std::min(chunk, std::max(1, Nt - 2));
+  for (int c = 0; c < nchains; ++c) {
+    Workspace* ws = wss[c];
+    if (ws->rowstore && ws->rowstore->nslots != chunk) {
+      cudaDeviceSynchronize();
+      cudaFree(ws->rowstore->data); cudaFree(ws->rowstore->dims); cudaFree(ws->rowstore->q); delete ws->rowstore;
+      ws->rowstore = nullptr;
+    }
+    if (!ws->rowstore) {
+      rc = ocmps_store_create(st->ctx, st->L, st->D, st->cap, chunk, &ws->rowstore);
+      if (rc) return rc;
+    }
+  }
   cplx* d_ovl = nullptr;
   double* d_norms = nullptr;
   CK(cudaMalloc(&d_ovl, sizeof(cplx) * (size_t)Nt * Nt));
@@ -1445,7 +1465,7 @@ int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* x
   // step per pass of the loop below, so this is longest-processing-time list scheduling of the rows onto the chains.
   std::vector<int> order(rows, rows + nrows);
   std::sort(order.begin(), order.end());
-  struct ChainState { int row = -1; int j = 0; };
+  struct ChainState { int row = -1; int j = 0; int filled = 0; int j0 = 0; };   // j0: time index of slot 0 of the open chunk
   std::atomic<int> next_row{0};
   std::vector<ChainState> cs(nchains);
   const int hw = (int)std::thread::hardware_concurrency();
@@ -1481,16 +1501,23 @@ int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* x
             lrc = fail(OCMPS_ERR_CUDA, "cudaMemcpyAsync failed"); break;
           }
           S.j = S.row + 1;
+          S.filled = 0; S.j0 = S.j;
           busy = true;
         } else {
           if (S.j >= Nt - 1) { S.row = -1; busy = true; continue; }
-          // one step forward and the overlap with xiH_j (:267-277)
-          lrc = step_enqueue(st, psiH[c], ws, u[S.j - 1], u[S.j], true, nullptr, 0, ws->stream);
+          // one step forward (:267-277); the slice goes to the chain's chunk store
+          lrc = step_enqueue(st, psiH[c], ws, u[S.j - 1], u[S.j], true, ws->rowstore, S.filled, ws->stream);
           if (lrc) break;
-          lrc = overlaps_async(ws, side_of_store(xiH_store, S.j), xiH_store->lay, side_of_mps(psiH[c]), psiH[c]->lay, 1, 0, ws->stream);
-          if (lrc) break;
-          if (cudaMemcpyAsync(d_ovl + (size_t)S.row * Nt + S.j, ws->d_out, sizeof(cplx), cudaMemcpyDeviceToDevice, ws->stream) != cudaSuccess) {
-            lrc = fail(OCMPS_ERR_CUDA, "cudaMemcpyAsync failed"); break;
+          ++S.filled;
+          if (S.filled == chunk || S.j == Nt - 2) {        // chunk full or row finished: overlaps with xiH_{j0 .. j0+filled-1}
+            lrc = overlaps_async(ws, side_of_store(xiH_store, S.j0), xiH_store->lay, side_of_store(ws->rowstore, 0), ws->rowstore->lay,
+                                 S.filled, 0, ws->stream);
+            if (lrc) break;
+            if (cudaMemcpyAsync(d_ovl + (size_t)S.row * Nt + S.j0, ws->d_out, sizeof(cplx) * S.filled, cudaMemcpyDeviceToDevice,
+                                ws->stream) != cudaSuccess) {
+              lrc = fail(OCMPS_ERR_CUDA, "cudaMemcpyAsync failed"); break;
+            }
+            S.filled = 0; S.j0 = S.j + 1;
           }
           ++S.j;
           busy = true;
