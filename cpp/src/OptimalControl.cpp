@@ -172,7 +172,7 @@ template <class TS> rowmat OptimalControl<TS>::calcHessian(const stdvec& u, cons
   for (size_t r = 1; r + 1 < N; ++r) rows.push_back((int)r);
   std::vector<Cplx> ovl(N * N, Cplx(0.0, 0.0));
   std::vector<double> norms(N, 0.0);
-  const int chains = (int)std::max<size_t>(1, std::min<size_t>(16, 4 * threadCount));
+  const int chains = (int)std::max<size_t>(1, std::min<size_t>(48, 12 * threadCount));   // rows in flight; measured optimum at chi=100
   if (!rows.empty())
     ocmps_check(ocmps_hessian_rows(timeStepper.handle(), psi_t->h, xiHlist->h, u.data(), (int)N, rows.data(), (int)rows.size(), chains,
                                    reinterpret_cast<double*>(ovl.data()), norms.data()), "ocmps_hessian_rows");

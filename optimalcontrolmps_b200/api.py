@@ -656,7 +656,7 @@ class OptimalControl:
         rows = np.array(list(range(1, N - 1)) if self.rows is None else list(self.rows), dtype=np.int32)
         ovl = np.zeros(2 * N * N)
         norms = np.zeros(N)
-        nch = self.hessian_chains or max(1, min(16, 4 * self.threadCount))
+        nch = self.hessian_chains or max(1, min(48, 12 * self.threadCount))   # measured (Nt=201, chi=100): 16 -> 25 s, 32 -> 16 s, 48 -> 14 s
         if rows.size:
             _lib.check(self.lib.ocmps_hessian_rows(self.timeStepper.h, self.psi_t.h, self.xiHlist.h, _pd(u), N, _pi(rows), rows.size,
                                                    nch, _pd(ovl), _pd(norms)))
