@@ -18,7 +18,7 @@ for rep in range(2):
     if o.xiHlist is None: o.xiHlist = st.new_store(Nt)
     _lib.check(lib.ocmps_store_apply_K(st.h, o.xi_t.h, Nt, o.xiHlist.h)); t2 = time.time()
     rows = np.arange(1, Nt - 1, dtype=np.int32); ovl = np.zeros(2 * Nt * Nt); norms = np.zeros(Nt)
-    _lib.check(lib.ocmps_hessian_rows(st.h, o.psi_t.h, o.xiHlist.h, _pd(u), Nt, _pi(rows), rows.size, 16, _pd(ovl), _pd(norms))); t3 = time.time()
+    _lib.check(lib.ocmps_hessian_rows(st.h, o.psi_t.h, o.xiHlist.h, _pd(u), Nt, _pi(rows), rows.size, int(sys.argv[2]) if len(sys.argv) > 2 else 48, _pd(ovl), _pd(norms))); t3 = time.time()
     print("sweeps+divT %.2f  store_apply_K %.2f  rows %.2f  (row-steps %d)" % (t1 - t0, t2 - t1, t3 - t2, (Nt - 2) * (Nt - 3) // 2))
 x = o.psi_t.get(Nt // 2)
 t0 = time.time()
