@@ -242,3 +242,28 @@ def test_batched_controls_match_single_evaluations(golden):
         assert abs(cs - res[k][0]) < 1e-12
         assert np.max(np.abs(np.array(gs) - np.array(res[k][1]))) < 1e-12
         assert abs(probs[k].getCost(ctrls[k], False) - cs) < 1e-12       # the problem is left in the cached state
+
+
+@pytest.mark.parametrize("L,d,Np,chi", [(6, 1, 3, 8), (6, 2, 6, 16), (7, 3, 7, 24), (5, 6, 6, 30), (4, 7, 9, 40), (10, 4, 10, 70)])
+def test_steps_match_oracle_for_every_local_dimension(L, d, Np, chi):
+    """The kernels are specialised at compile time on the local dimension D = d+1 (2..8) and on the block shapes; walk
+    through all of them: two forward and one backward Trotter step of a random number-conserving MPS against the oracle
+    (identical bond dimensions, same state to 1e-9, charges conserved)."""
+    import optimalcontrolmps_b200 as oc
+    from oracle import bh_mps as ob
+    from conftest import random_symmetric_mps
+    psi = random_symmetric_mps(L, d + 1, Np, chi, seed=100 * L + d)
+    cutoff = 1e-9
+    so = ob.BHStepper(L, d + 1, 1.0, 2e-2, ob.TruncArgs(cutoff=cutoff, maxm=chi))
+    st = oc.BH_tDMRG(oc.BoseHubbard(L, d), 1.0, 2e-2, oc.Args("Cutoff=", cutoff, "Maxm=", chi),
+                     chi_cap=max(chi, max(psi.bond_dims())))
+    dev = st.to_device(to_host(psi))
+    po = psi.copy()
+    for (a, b, fwd) in [(2.0, 3.0, True), (3.0, 5.0, True), (5.0, 4.0, False)]:
+        so.step(po, a, b, fwd)
+        st.step(dev, a, b, fwd)
+        got = to_oracle(dev.download())
+        assert got.bond_dims() == po.bond_dims()
+        assert abs(abs(ob.overlap(po, got)) - 1.0) < 1e-9
+        assert abs(dev.norm() - 1.0) < 1e-12
+        assert got.check_charges() == 0.0
