@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "BH_nlp.hpp"
+#include "correlations.hpp"
 #include "BH_tDMRG.hpp"
 #include "ControlBasisFactory.hpp"
 #include "OptimalControl.hpp"
@@ -83,6 +84,18 @@ int main(int argc, char** argv) {
   IQMPS psi = psi_i;
   stepper.step(psi, u[0], u[1], true);
   check(std::fabs(norm(psi) - 1.0) < 1e-12, "BH_tDMRG::step keeps the norm", std::fabs(norm(psi) - 1.0));
+  {   // include/correlations.hpp: <N_j> of the evolved state adds up to the particle number; NN = N(N-1) + N
+    auto nj = expectationValues(sites, psi, "N"), n2 = expectationValues(sites, psi, "NN"), nn1 = expectationValues(sites, psi, "N(N-1)");
+    auto n0 = expectationValues(sites, psi_i, "N");
+    double tot = 0.0, tot0 = 0.0, dev = 0.0;
+    for (size_t j = 0; j < nj.size(); ++j) {
+      tot += nj[j].real(); tot0 += n0[j].real();
+      dev = std::max(dev, std::fabs(n2[j].real() - nn1[j].real() - nj[j].real()));
+    }
+    check(std::fabs(tot - tot0) < 1e-10 && std::fabs(tot0 - std::round(tot0)) < 1e-8, "expectationValues: particle number conserved", std::fabs(tot - tot0));
+    check(dev < 1e-11, "expectationValues: <NN> = <N(N-1)> + <N>", dev);
+    check(std::abs(expectationValue(sites, psi, "N", 2) - nj[1]) < 1e-14, "expectationValue(site 2)", 0.0);
+  }
   IQMPS kpsi = exactApplyMPO(stepper.propagatorDeriv(u[0]), psi, stepper.getArgs());
   const Cplx k1 = overlapC(psi, kpsi), k2 = overlapC(psi, stepper.propagatorDeriv(u[0]), psi);
   check(std::abs(k1 - k2) < 5e-3 * std::abs(k2), "<psi|K psi> ~ <psi|K|psi> (up to the Maxm truncation)", std::abs(k1 - k2));

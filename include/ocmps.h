@@ -111,6 +111,14 @@ int ocmps_backward_sweep_divT(ocmps_stepper* st, ocmps_mps* psi_target, const do
 int ocmps_store_overlaps(ocmps_store* store, ocmps_mps* bra, int Nt, double* out /* 2*Nt */);
 /* divT[i] = <xi_i|K|psi_i> (calcDivT :410-419) */
 int ocmps_store_divT(ocmps_store* xi_store, ocmps_store* psi_store, int Nt, double* out /* 2*Nt */);
+/* Observables on resident slices (include/correlations.hpp:99-117 expectationValue / expectationValues; used per slice at
+ * main/OptimizeRamp.cpp:144-158): out[((z*L + j)*nops + k] = <psi_z| O_k at site j |psi_z> for the slices first..first+count-1,
+ * every site j and `nops` (1..7) site operators that are diagonal in the boson number, given by their diagonals
+ * op_diag[k*D + n] (N: n; N(N-1): n(n-1); NN: n^2 -- include/BH_sites.h:129-171).  Not divided by the norm, like the reference.
+ * The slices must have their orthogonality centre at site 1 (every slice written by the sweeps has); norm2 (may be NULL)
+ * receives <psi_z|psi_z> as seen from every site, count*L values that all equal the norm when that holds. */
+int ocmps_store_site_expectations(ocmps_store* store, int first, int count, const double* op_diag, int nops,
+                                  double* out /* count*L*nops */, double* norm2 /* count*L or NULL */);
 /* xiHlist[i] = exactApplyMPO(K, xi_t[i], args) for all i (:300-303) */
 int ocmps_store_apply_K(ocmps_stepper* st, ocmps_store* in, int Nt, ocmps_store* out);
 /* calcHessianRow (:252-279) for `nrows` rows listed in `rows`: for every row r the raw ingredients are returned,

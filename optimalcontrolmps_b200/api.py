@@ -207,6 +207,24 @@ class SliceStore:
         _lib.check(self.ctx.lib.ocmps_store_bond_dims(self.h, _pi(out)))
         return out
 
+    # site operators of include/BH_sites.h:129-171 that are diagonal in the boson number
+    SITE_OPS = {"N": lambda n: n, "N(N-1)": lambda n: n * (n - 1.0), "NN": lambda n: n * n, "Id": lambda n: 1.0 + 0.0 * n}
+
+    def expectationValues(self, opnames=("N",), first=0, count=None, return_norm=False):
+        """``expectationValues(sites, psi, opname)`` (include/correlations.hpp:109-117) for every resident slice at once:
+        array [slice, site, op] of <psi| O_site |psi> (not divided by the norm, like the reference).  Operators by name
+        (N, N(N-1), NN, Id) or as explicit diagonals of length D."""
+        count = self.nslots - first if count is None else count
+        n = np.arange(self.D, dtype=float)
+        diags = np.array([self.SITE_OPS[o](n) if isinstance(o, str) else np.asarray(o, dtype=float) for o in opnames], dtype=float)
+        if diags.shape != (len(opnames), self.D):
+            raise ValueError("operator diagonals must have length D")
+        diags = np.ascontiguousarray(diags)
+        out = np.zeros((count, self.L, len(opnames)))
+        nrm = np.zeros((count, self.L))
+        _lib.check(self.ctx.lib.ocmps_store_site_expectations(self.h, first, count, _pd(diags), len(opnames), _pd(out), _pd(nrm)))
+        return (out, nrm) if return_norm else out
+
 
 def overlapC(a: DeviceMPS, b: DeviceMPS) -> complex:
     """<a|b>, first argument conjugated (ITensor ``overlapC``)."""

@@ -264,6 +264,45 @@ __global__ void overlap_plan_kernel(GemmDesc* descs, OvlSide bra, OvlSide ket, i
   }
 }
 
+// Local expectation values on top of the transfer-matrix chain of <psi|psi> (include/correlations.hpp:99-117):
+//   out[z][site][k] = sum_{l',s,r} conj(A[l',s,r]) T[l',s,r] op_k[s],   T = E_left . A  (the T gemm of this site)
+// for diagonal site operators op_k (N, N(N-1), N^2 ... are all diagonal in the boson number).  Exact when the sites to
+// the right of `site` are right-orthonormal, which is how the sweeps leave every slice (centre at site 1); k = 0 is
+// reserved for the identity, so out[z][site][0] = <psi|psi> is the built-in check of that precondition.
+// One CTA per batch entry; fixed-order tree reduction (deterministic).
+constexpr int EXPECT_MAX_OPS = 8;
+__global__ void __launch_bounds__(256) overlap_local_expect_kernel(const GemmDesc* __restrict__ descs, OvlSide bra, int site, int D,
+                                                                   const double* __restrict__ ops, int nops, double* __restrict__ out,
+                                                                   int L) {
+  __shared__ double red[EXPECT_MAX_OPS][256];
+  const int z = blockIdx.x;
+  const GemmDesc g = descs[z];
+  const int aL = g.M, N = g.N, bR = N / D;
+  const cplx* __restrict__ T = g.C;
+  const cplx* __restrict__ A = side_site(bra, z, site);
+  double acc[EXPECT_MAX_OPS];
+#pragma unroll
+  for (int k = 0; k < EXPECT_MAX_OPS; ++k) acc[k] = 0.0;
+  const long long total = (long long)aL * N;
+  for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+    const int sx = (int)((e % N) / bR);
+    const cplx a = A[e], t = T[e];
+    const double w = a.x * t.x + a.y * t.y;          // Re(conj(a) t); the imaginary parts cancel in the sum
+#pragma unroll
+    for (int k = 0; k < EXPECT_MAX_OPS; ++k)
+      if (k < nops) acc[k] += w * ops[k * D + sx];
+  }
+#pragma unroll
+  for (int k = 0; k < EXPECT_MAX_OPS; ++k) red[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o)
+      for (int k = 0; k < nops; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + o];
+    __syncthreads();
+  }
+  if ((int)threadIdx.x < nops) out[((long long)z * L + site) * nops + threadIdx.x] = red[threadIdx.x][0];
+}
+
 __global__ void overlap_init_kernel(cplx* E, long long e_stride, int batch, int withK) {
   const int z = blockIdx.x * blockDim.x + threadIdx.x;
   if (z >= batch) return;
@@ -397,6 +436,10 @@ void launch_unpack_copy(const cplx* src_base, SitePtrs dst, SiteOffs offs, const
 void launch_overlap_plan(GemmDesc* descs, const OvlSide& bra, const OvlSide& ket, int site, int batch, int D, int withK,
                          cplx* E_in, cplx* E_out, cplx* T, long long e_stride, long long t_stride, cudaStream_t s) {
   overlap_plan_kernel<<<(batch + 63) / 64, 64, 0, s>>>(descs, bra, ket, site, batch, D, withK, E_in, E_out, T, e_stride, t_stride);
+}
+void launch_overlap_local_expect(const GemmDesc* descs, const OvlSide& bra, int site, int batch, int D, const double* ops, int nops,
+                                 double* out, int L, cudaStream_t s) {
+  overlap_local_expect_kernel<<<batch, 256, 0, s>>>(descs, bra, site, D, ops, nops, out, L);
 }
 void launch_overlap_init(cplx* E, long long e_stride, int batch, int withK, cudaStream_t s) {
   overlap_init_kernel<<<(batch + 63) / 64, 64, 0, s>>>(E, e_stride, batch, withK);

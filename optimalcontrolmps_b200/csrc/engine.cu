@@ -1380,6 +1380,67 @@ int ocmps_store_divT(ocmps_store* xi_store, ocmps_store* psi_store, int Nt, doub
   return store_overlaps_impl(xi_store, nullptr, psi_store, Nt, 1, out);
 }
 
+// <psi_z| op_k at site j |psi_z> for the slices first .. first+count-1, all sites, `nops` diagonal site operators
+// (include/correlations.hpp:99-117 `expectationValue(s)`: psi.position(j), local contraction -- here one pass of the
+// transfer-matrix chain per slice, batched over the slices; see overlap_local_expect_kernel for the gauge precondition).
+int ocmps_store_site_expectations(ocmps_store* store, int first, int count, const double* op_diag, int nops, double* out,
+                                  double* norm2) {
+  if (!store || !op_diag || !out || count < 1 || first < 0 || first + count > store->nslots)
+    return fail(OCMPS_ERR_INVALID, "bad argument");
+  if (nops < 1 || nops + 1 > OCMPS_EXPECT_MAX_OPS) return fail(OCMPS_ERR_INVALID, "site_expectations: 1..7 operators per call");
+  ocmps_ctx* ctx = store->ctx;
+  const Layout& lay = store->lay;
+  const int L = lay.L, D = lay.D, nk = nops + 1;
+  CK(cudaSetDevice(ctx->dev));
+  Workspace* ws = nullptr;
+  int rc = get_ws(ctx, L, D, lay.cap, 0, &ws);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  std::vector<double> h_ops((size_t)nk * D);
+  for (int s = 0; s < D; ++s) h_ops[s] = 1.0;                               // slot 0: identity
+  for (int k = 0; k < nops; ++k)
+    for (int s = 0; s < D; ++s) h_ops[(size_t)(k + 1) * D + s] = op_diag[(size_t)k * D + s];
+  const int chunk = 64;
+  double *d_ops = nullptr, *d_res = nullptr;
+  CK(cudaMalloc(&d_ops, sizeof(double) * h_ops.size()));
+  CK(cudaMalloc(&d_res, sizeof(double) * (size_t)chunk * L * nk));
+  CK(cudaMemcpy(d_ops, h_ops.data(), sizeof(double) * h_ops.size(), cudaMemcpyHostToDevice));
+  std::vector<double> h_res((size_t)chunk * L * nk);
+  cudaStream_t s = ws->stream;
+  for (int z0 = 0; z0 < count && !rc; z0 += chunk) {
+    const int nb = std::min(chunk, count - z0);
+    const OvlSide side = side_of_store(store, first + z0);
+    rc = ensure_overlap_bufs(ws, nb, lay.cap, lay.cap);
+    if (rc) break;
+    launch_overlap_init(ws->E[0], ws->e_stride, nb, 0, s);
+    int cur = 0;
+    for (int j = 0; j < L; ++j) {
+      launch_overlap_plan(ws->odescs, side, side, j, nb, D, 0, ws->E[cur], ws->E[1 - cur], ws->T, ws->e_stride, ws->t_stride, s);
+      launch_zgemm(ws->odescs, nb, lay.capb[j], D * lay.capb[j + 1], s);
+      launch_overlap_local_expect(ws->odescs, side, j, nb, D, d_ops, nk, d_res, L, s);
+      launch_zgemm(ws->odescs + nb, nb, lay.capb[j + 1], lay.capb[j + 1], s);
+      cur = 1 - cur;
+      g_ocmps_launches += 4;
+    }
+    g_ocmps_launches += 1;
+    if (cudaMemcpyAsync(h_res.data(), d_res, sizeof(double) * (size_t)nb * L * nk, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+      rc = fail(OCMPS_ERR_CUDA, "site_expectations: copy failed");
+      break;
+    }
+    for (int z = 0; z < nb; ++z)
+      for (int j = 0; j < L; ++j) {
+        const double* r = &h_res[((size_t)z * L + j) * nk];
+        if (norm2) norm2[(size_t)(z0 + z) * L + j] = r[0];
+        for (int k = 0; k < nops; ++k) out[((size_t)(z0 + z) * L + j) * nops + k] = r[k + 1];
+      }
+  }
+  cudaFree(d_ops); cudaFree(d_res);
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  return OCMPS_OK;
+}
+
 int ocmps_store_apply_K(ocmps_stepper* st, ocmps_store* in, int Nt, ocmps_store* out) {
   if (!st || !in || !out || Nt < 1 || Nt > in->nslots || Nt > out->nslots) return fail(OCMPS_ERR_INVALID, "bad argument");
   int rc = check_shapes(st, in->lay, "store_apply_K");

@@ -159,6 +159,9 @@ struct OvlSide {              // how to find site tensors / dims of batch entry 
 void launch_overlap_plan(GemmDesc* descs, const OvlSide& bra, const OvlSide& ket, int site, int batch, int D, int withK,
                          cplx* E_in, cplx* E_out, cplx* T, long long e_stride, long long t_stride, cudaStream_t s);
 void launch_overlap_init(cplx* E, long long e_stride, int batch, int withK, cudaStream_t s);
+constexpr int OCMPS_EXPECT_MAX_OPS = 8;   // site operators per call of the expectation-value chain (slot 0 = identity)
+void launch_overlap_local_expect(const GemmDesc* descs, const OvlSide& bra, int site, int batch, int D, const double* ops, int nops,
+                                 double* out, int L, cudaStream_t s);
 void launch_overlap_kfix(cplx* T, long long t_stride, const GemmDesc* descs, int batch, int D, int max_elems, cudaStream_t s);
 void launch_overlap_final(const cplx* E, long long e_stride, int batch, int withK, cplx* out, cudaStream_t s);
 

@@ -267,3 +267,28 @@ def test_steps_match_oracle_for_every_local_dimension(L, d, Np, chi):
         assert abs(abs(ob.overlap(po, got)) - 1.0) < 1e-9
         assert abs(dev.norm() - 1.0) < 1e-12
         assert got.check_charges() == 0.0
+
+
+def test_site_expectation_values_on_resident_slices(golden):
+    """Observables on the HBM-resident slices (include/correlations.hpp:99-117) against the oracle: <N_j>, <N_j(N_j-1)>,
+    <N_j^2> of every slice of a forward sweep; the particle number is conserved; the built-in norm check holds."""
+    g = golden
+    oc, z, st, N = g["oc"], g["z"], g["st"], g["N"]
+    from oracle import observables as obs
+    ocg = oc.OptimalControl(to_host(g["target"]), to_host(g["init"]), st, N, g["gamma"])
+    u = list(z["u"])
+    ocg.getCost(u)                                        # forward sweep: psi_t resident
+    vals, nrm = ocg.psi_t.expectationValues(("N", "N(N-1)", "NN"), return_norm=True)
+    assert vals.shape == (N, g["L"], 3)
+    assert np.max(np.abs(nrm - 1.0)) < 1e-12              # centre at site 1 in every slice, unit norm
+    npart = float(np.sum(obs.expectation_values(g["init"], np.arange(g["d"] + 1, dtype=float))))
+    assert np.max(np.abs(vals[:, :, 0].sum(axis=1) - npart)) < 1e-10
+    n = np.arange(g["d"] + 1, dtype=float)
+    for i in sorted(set([0, 1, N // 3, N // 2, N - 1])):
+        po = to_oracle(ocg.psi_t.get(i).download())
+        for k, diag in enumerate((n, n * (n - 1.0), n * n)):
+            want = obs.expectation_values(po, diag)
+            assert np.max(np.abs(vals[i, :, k] - want)) < 1e-11
+    assert np.max(np.abs(vals[:, :, 2] - vals[:, :, 1] - vals[:, :, 0])) < 1e-11      # NN = N(N-1) + N
+    sub = ocg.psi_t.expectationValues(("N",), first=2, count=3)
+    assert np.array_equal(sub[:, :, 0], vals[2:5, :, 0])

@@ -203,3 +203,26 @@ def test_schedule_touches_every_bond_once():
     for L in (2, 3, 4, 5, 6, 7, 20):
         gates = ob.gate_order(L)
         assert sorted(gates) == [(i, i + 1) for i in range(1, L)]
+
+
+def test_observables_restatement_on_exact_states():
+    """oracle.observables against dense state vectors: <N_j> of a number-conserving state sums to the particle number,
+    and every entry equals the expectation value computed from the full state vector."""
+    import itertools
+    from oracle import bh_mps as ob, observables as obs
+    L, D, Np = 4, 3, 3
+    rng = np.random.default_rng(5)
+    confs = [c for c in itertools.product(range(D), repeat=L) if sum(c) == Np]
+    vec = np.zeros((D,) * L, dtype=complex)
+    for c in confs:
+        vec[c] = rng.normal() + 1j * rng.normal()
+    vec /= np.linalg.norm(vec)
+    psi = ob.mps_from_statevector(vec.reshape(-1), L, D)
+    n = np.arange(D, dtype=float)
+    got = obs.expectation_values(psi, n)
+    want = [float(sum(abs(vec[c]) ** 2 * c[j] for c in confs)) for j in range(L)]
+    assert np.allclose(got, want, atol=1e-12)
+    assert abs(got.sum() - Np) < 1e-12
+    got2 = obs.expectation_values(psi, n * (n - 1))
+    want2 = [float(sum(abs(vec[c]) ** 2 * c[j] * (c[j] - 1) for c in confs)) for j in range(L)]
+    assert np.allclose(got2, want2, atol=1e-12)
