@@ -7,13 +7,19 @@
 // orthogonality centre with block SVDs (A.4).  The eigenvalues of the Gram matrix are the squared
 // singular values of theta and its eigenvectors are the singular vectors, so each charge block
 // M (len x nv, columns = the vectors to orthogonalise) is decomposed as M = U D Z directly:
-//   1. Householder QR with column pivoting, M P = Q R, in shared memory (rank revealing; k <= min(len, nv));
+//   1. Householder QR with column pivoting, M P = Q R, in shared memory (rank revealing; k <= min(len, nv))
+//      -- jacobi_blocks_kernel, step code in qr_step_cached;
 //   2. Hestenes one-sided Jacobi on the k rows of R (Drmac-Veselic preconditioning: 6-7 sweeps instead of
 //      the ~20 plain cyclic Jacobi needs on these strongly graded spectra): pairs of rows are rotated
 //      until every Gram entry <r_p|r_q> vanishes; one half-warp per pair, dot products by shuffles;
-//      the Gram diagonal (squared norms) is the spectrum the truncation rule sees;
-//   3. after the global truncation, only the kept left vectors are formed, u_j = M z_j^H / |M z_j^H|.
-// One CTA per block.
+//      the Gram diagonal (squared norms) is the spectrum the truncation rule sees
+//      -- jacobi_rot_kernel (rows register resident, jacobi_sweep_blocked) for blocks with at most 64 rows of R,
+//      the generic loops at the end of jacobi_blocks_kernel otherwise;
+//   3. global truncation over all blocks (truncate_kernel);
+//   4. only the kept left vectors are formed, u_j = M z_j^H / |M z_j^H| (build_factors_kernel; for gauge moves it
+//      also pushes the carry matrix into the neighbouring site tensor).
+// One CTA per block in 1 and 2.  Both are bound by instruction issue and dependent latency on that one SM (see
+// profiles/r01_kernel_shares.md), so the code is specialised at compile time on the block shape wherever it is hot.
 #include <cstdio>
 #include "ocmps_internal.h"
 
