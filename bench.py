@@ -19,6 +19,7 @@ workload; the reference's own ITensor build cannot be produced here.
 import argparse
 import json
 import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA starts: one hardware queue per chain stream (see the package __init__)
 import subprocess
 import sys
 import threading

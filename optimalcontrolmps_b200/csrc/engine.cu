@@ -844,6 +844,9 @@ int ocmps_profile_read(double* out4) { if (!out4) return fail(OCMPS_ERR_INVALID,
 
 int ocmps_ctx_create(int device, ocmps_ctx** out) {
   if (!out) return fail(OCMPS_ERR_INVALID, "null out");
+  // One hardware queue per chain stream where possible (default 8: chains on aliased queues serialise).  Only effective if
+  // this is the first CUDA call of the process; a value set by the user is kept.
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) return fail(OCMPS_ERR_CUDA, "no CUDA device available (libocmps has no CPU fallback)");
