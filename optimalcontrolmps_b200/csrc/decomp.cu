@@ -600,7 +600,6 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
     const int pv = pcur[bpos];             // physical slot of the pivot vector
     const int pj = pcur[j];
     const cplx* x = Y + pv * len;          // Householder vector: x[j..len), with x[j] replaced by v0
-    const int nrem = len - j;                              // components j .. len-1
     unsigned long long* knext = &s_key[(j + 1) % 3];
     {
     // generic path: every warp computes the exact norm of the pivot vector
@@ -966,13 +965,13 @@ __global__ void __launch_bounds__(1024) truncate_kernel(DecompArgs a, DecompBuff
   __shared__ double sWarp[32];
   __shared__ int sWarpCnt[33];
   __shared__ double s_docut, s_kept;
-  __shared__ int s_total, s_nfinal;
+  __shared__ int s_nfinal;
   DecompWork* w = b.dw;
   const int nv = w->nvtot;
   const int nblocks = w->nblocks;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < nblocks; i += blockDim.x) sBlkOff[i] = w->blk[i].p_off;
-  if (tid == 0) { s_total = 0; s_nfinal = 0; s_docut = 0.0; }
+  if (tid == 0) { s_nfinal = 0; s_docut = 0.0; }
   // ---- compaction (order preserving): thread t owns entries 2t, 2t+1 ----
   const int i0 = 2 * tid, i1 = i0 + 1;
   const double p0 = i0 < nv ? b.P[i0] : 0.0, p1 = i1 < nv ? b.P[i1] : 0.0;

@@ -469,7 +469,7 @@ static bool fused_push_enabled() {
 
 // the kernel sequence of one Trotter step in place on `m` (all step-dependent values are read from ws->d_params)
 void run_step_body(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, cudaStream_t s, int op_begin = 0, int op_end = 1 << 30) {
-  const int L = st->L, D = st->D;
+  const int D = st->D;
   const Layout& lay = m->lay;
   const StepParams* sp = ws->d_params;
   TruncParams tpg{st->cutoff, st->maxm, 1, st->rel_cutoff, 0, 1};
