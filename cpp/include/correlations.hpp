@@ -4,7 +4,8 @@
 // as in the reference.  The state is copied into a one-slot slice store and evaluated by the batched transfer-matrix
 // chain (ocmps_store_site_expectations); that chain needs the orthogonality centre at site 1, which every state that
 // went through BH_tDMRG::step has -- any other gauge is detected and reported.
-// Not provided (ITensor-only post-processing): correlationFunction/Matrix/Term, entanglementEntropy.
+// entanglementEntropy(sites, psi) (:119-148) is provided as well (gauge moves of the engine, spectrum per bond).
+// Not provided (ITensor-only post-processing): correlationFunction/Matrix/Term.
 #ifndef OCMPS_CORRELATIONS_HPP
 #define OCMPS_CORRELATIONS_HPP
 
@@ -51,6 +52,20 @@ inline std::vector<itensor::Cplx> expectationValues(itensor::SiteSet const& site
 
 inline itensor::Cplx expectationValue(itensor::SiteSet const& sites, itensor::IQMPS& psi, std::string const& opname, int i) {
   return expectationValues(sites, psi, opname).at(i - 1);       // sites are 1-based in the reference
+}
+
+inline std::vector<double> entanglementEntropy(itensor::SiteSet const& sites, itensor::IQMPS& psi) {
+  using namespace itensor;
+  const int L = psi.N(), D = psi.D();
+  (void)sites;
+  ocmps_store* store = nullptr;
+  ocmps_check(ocmps_store_create(default_context(), L, D, psi.capacity(), 1, &store), "ocmps_store_create");
+  std::vector<double> S(L > 1 ? L - 1 : 0);
+  int rc = ocmps_store_put(store, 0, psi.handle());
+  if (!rc && L > 1) rc = ocmps_store_entanglement_entropy(store, 0, 1, S.data());
+  ocmps_store_destroy(store);
+  ocmps_check(rc, "ocmps_store_entanglement_entropy");
+  return S;
 }
 
 #endif

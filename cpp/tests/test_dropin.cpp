@@ -95,6 +95,10 @@ int main(int argc, char** argv) {
     check(std::fabs(tot - tot0) < 1e-10 && std::fabs(tot0 - std::round(tot0)) < 1e-8, "expectationValues: particle number conserved", std::fabs(tot - tot0));
     check(dev < 1e-11, "expectationValues: <NN> = <N(N-1)> + <N>", dev);
     check(std::abs(expectationValue(sites, psi, "N", 2) - nj[1]) < 1e-14, "expectationValue(site 2)", 0.0);
+    auto SvN = entanglementEntropy(sites, psi);
+    bool sok = (int)SvN.size() == L - 1;
+    for (double x : SvN) sok = sok && x > -1e-12 && x < std::log((double)cap) + 1e-9;
+    check(sok, "entanglementEntropy: L-1 values within [0, ln chi]", SvN.empty() ? 0.0 : SvN[SvN.size() / 2]);
   }
   IQMPS kpsi = exactApplyMPO(stepper.propagatorDeriv(u[0]), psi, stepper.getArgs());
   const Cplx k1 = overlapC(psi, kpsi), k2 = overlapC(psi, stepper.propagatorDeriv(u[0]), psi);

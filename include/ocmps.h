@@ -119,6 +119,10 @@ int ocmps_store_divT(ocmps_store* xi_store, ocmps_store* psi_store, int Nt, doub
  * receives <psi_z|psi_z> as seen from every site, count*L values that all equal the norm when that holds. */
 int ocmps_store_site_expectations(ocmps_store* store, int first, int count, const double* op_diag, int nops,
                                   double* out /* count*L*nops */, double* norm2 /* count*L or NULL */);
+/* Entanglement entropy of every bond (include/correlations.hpp:119-148: psi.position(i), SVD of the two-site wavefunction,
+ * S = -sum_{p > 1e-12} p ln p over the density-matrix eigenvalues): out[z*(L-1) + (i-1)] for bond i = 1..L-1 of the slices
+ * first..first+count-1.  Works on a copy (the store is not modified); slices must have their centre at site 1. */
+int ocmps_store_entanglement_entropy(ocmps_store* store, int first, int count, double* out /* count*(L-1) */);
 /* xiHlist[i] = exactApplyMPO(K, xi_t[i], args) for all i (:300-303) */
 int ocmps_store_apply_K(ocmps_stepper* st, ocmps_store* in, int Nt, ocmps_store* out);
 /* calcHessianRow (:252-279) for `nrows` rows listed in `rows`: for every row r the raw ingredients are returned,

@@ -207,6 +207,14 @@ class SliceStore:
         _lib.check(self.ctx.lib.ocmps_store_bond_dims(self.h, _pi(out)))
         return out
 
+    def entanglementEntropy(self, first=0, count=None):
+        """``entanglementEntropy(sites, psi)`` (include/correlations.hpp:119-148) for the resident slices: array
+        [slice, bond] of the von Neumann entropies -sum_{p>1e-12} p ln p of the L-1 bonds."""
+        count = self.nslots - first if count is None else count
+        out = np.zeros((count, self.L - 1))
+        _lib.check(self.ctx.lib.ocmps_store_entanglement_entropy(self.h, first, count, _pd(out)))
+        return out
+
     # site operators of include/BH_sites.h:129-171 that are diagonal in the boson number
     SITE_OPS = {"N": lambda n: n, "N(N-1)": lambda n: n * (n - 1.0), "NN": lambda n: n * n, "Id": lambda n: 1.0 + 0.0 * n}
 

@@ -1390,6 +1390,29 @@ void debug_jacobi_counters(unsigned long long* out, bool reset) {
   if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_jac_dbg, z, sizeof(z)); }
 }
 
+// von Neumann entropy of the spectrum the last decomposition left in b.P (include/correlations.hpp:119-148):
+// S = -sum_{p > 1e-12} p ln p over the squared singular values of all charge blocks.  One CTA, fixed-order tree.
+__global__ void __launch_bounds__(256) spectrum_entropy_kernel(DecompBuffers b, double* out) {
+  __shared__ double red[256];
+  const int nv = b.dw->nvtot;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nv; i += 256) {
+    const double p = b.P[i];
+    if (p > 1e-12) acc -= p * log(p);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = red[0];
+}
+
+void launch_spectrum_entropy(const DecompBuffers& b, double* out, cudaStream_t s) {
+  spectrum_entropy_kernel<<<1, 256, 0, s>>>(b, out);
+}
+
 void launch_decomp_setup(const DecompArgs& a, const DecompBuffers& b, cudaStream_t s) {
   decomp_setup_kernel<<<1, SETUP_THREADS, 0, s>>>(a, b);
 }

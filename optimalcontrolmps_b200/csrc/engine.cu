@@ -1444,6 +1444,56 @@ int ocmps_store_site_expectations(ocmps_store* store, int first, int count, cons
   return OCMPS_OK;
 }
 
+// Entanglement entropy of every bond of the slices first .. first+count-1 (include/correlations.hpp:119-148:
+// psi.position(i), SVD of the two-site wavefunction, S = -sum_{p>1e-12} p ln p over the density-matrix eigenvalues).
+// The orthogonality centre of a copy of the slice is moved from site 1 to site L with the engine's own gauge moves;
+// the spectrum of the move across bond i is the Schmidt spectrum of that bond.  The store is not modified.
+int ocmps_store_entanglement_entropy(ocmps_store* store, int first, int count, double* out) {
+  if (!store || !out || count < 1 || first < 0 || first + count > store->nslots) return fail(OCMPS_ERR_INVALID, "bad argument");
+  ocmps_ctx* ctx = store->ctx;
+  const Layout& lay = store->lay;
+  const int L = lay.L, D = lay.D;
+  if (L < 2) return fail(OCMPS_ERR_INVALID, "entanglement_entropy needs L >= 2");
+  CK(cudaSetDevice(ctx->dev));
+  Workspace* ws = nullptr;
+  int rc = get_ws(ctx, L, D, lay.cap, 0, &ws);
+  if (rc) return rc;
+  CK(cudaDeviceSynchronize());
+  double* d_out = nullptr;
+  CK(cudaMalloc(&d_out, sizeof(double) * (size_t)count * (L - 1)));
+  cudaStream_t s = ws->stream;
+  ocmps_mps* m = ws->work;
+  TruncParams tpo{MIN_CUT, MAX_M, 1, 0, 0, 0};
+  for (int z = 0; z < count && !rc; ++z) {
+    rc = store_get_async(store, first + z, m, s);
+    if (rc) break;
+    for (int b = 1; b <= L - 1; ++b) {
+      const int j = b - 1, jn = b;
+      DecompArgs a;
+      a.D = D; a.kind = DK_ORTH_LEFT;
+      a.dimNew = m->dim(b); a.qNew = m->q(b); a.partner = ws->cbuf;
+      a.dimL = m->dim(b - 1); a.dimR = m->dim(b); a.qL = m->q(b - 1); a.qR = m->q(b);
+      a.X = m->site(j); a.iso = m->other(j);
+      a.nb_in = m->site(jn); a.nb_out = m->other(jn); a.dimNb = m->dim(b + 1);
+      a.qNb = fused_push_enabled() ? m->q(b + 1) : nullptr;
+      tpo.cap = lay.capb[b];
+      run_decomp(ws, a, tpo, lay.capb[b], lay.capb[b - 1], lay.capb[b], s);
+      if (!a.qNb) { launch_zgemm(ws->db.descs + 1, 1, lay.capb[b], D * lay.capb[b + 1], s); g_ocmps_launches += 1; }
+      launch_spectrum_entropy(ws->db, d_out + (size_t)z * (L - 1) + (b - 1), s);
+      g_ocmps_launches += 1;
+      m->cur[j] ^= 1; m->cur[jn] ^= 1;
+    }
+  }
+  if (!rc && (cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)count * (L - 1), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+              cudaStreamSynchronize(s) != cudaSuccess))
+    rc = fail(OCMPS_ERR_CUDA, "entanglement_entropy: copy failed");
+  cudaStreamSynchronize(s);
+  cudaFree(d_out);
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  return check_status(ctx);
+}
+
 int ocmps_store_apply_K(ocmps_stepper* st, ocmps_store* in, int Nt, ocmps_store* out) {
   if (!st || !in || !out || Nt < 1 || Nt > in->nslots || Nt > out->nslots) return fail(OCMPS_ERR_INVALID, "bad argument");
   int rc = check_shapes(st, in->lay, "store_apply_K");

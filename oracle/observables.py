@@ -24,3 +24,21 @@ def expectation_values(psi, op_diag):
         v = np.einsum("xy,xsa,s,ysb,ab->", left[j], A[j].conj(), op, A[j], right[j + 1])
         out[j] = v.real
     return out
+
+
+def entanglement_entropy(psi):
+    """von Neumann entropies of the L-1 bonds, include/correlations.hpp:119-148: position(i), SVD of the two-site
+    wavefunction, S = -sum_{p > 1e-12} p ln p over the density-matrix eigenvalues p = sigma^2 (not renormalised).
+    With the centre at site i the site tensor as a (left x physical) x right matrix has the same singular values as the
+    two-site wavefunction (site i+1 is right-orthonormal), so a copy is gauged site by site and that matrix is decomposed."""
+    phi = psi.copy()
+    L = len(phi.A)
+    out = np.zeros(L - 1)
+    for i in range(1, L):
+        phi.position(i)
+        a = phi.A[i - 1]
+        sv = np.linalg.svd(a.reshape(a.shape[0] * a.shape[1], a.shape[2]), compute_uv=False)
+        p = sv ** 2
+        p = p[p > 1e-12]
+        out[i - 1] = float(-(p * np.log(p)).sum())
+    return out

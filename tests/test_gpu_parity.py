@@ -292,3 +292,20 @@ def test_site_expectation_values_on_resident_slices(golden):
     assert np.max(np.abs(vals[:, :, 2] - vals[:, :, 1] - vals[:, :, 0])) < 1e-11      # NN = N(N-1) + N
     sub = ocg.psi_t.expectationValues(("N",), first=2, count=3)
     assert np.array_equal(sub[:, :, 0], vals[2:5, :, 0])
+
+
+def test_entanglement_entropy_on_resident_slices(golden):
+    """Bond entropies of the resident slices (include/correlations.hpp:119-148) against the oracle; the store is unchanged."""
+    g = golden
+    oc, z, st, N = g["oc"], g["z"], g["st"], g["N"]
+    from oracle import observables as obs
+    ocg = oc.OptimalControl(to_host(g["target"]), to_host(g["init"]), st, N, g["gamma"])
+    ocg.getCost(list(z["u"]))
+    dims = np.array(ocg.psi_t.bond_dims())
+    S = ocg.psi_t.entanglementEntropy()
+    assert S.shape == (N, g["L"] - 1)
+    assert np.array_equal(np.array(ocg.psi_t.bond_dims()), dims)
+    for i in sorted(set([0, 1, N // 2, N - 1])):
+        want = obs.entanglement_entropy(to_oracle(ocg.psi_t.get(i).download()))
+        assert np.max(np.abs(S[i] - want)) < 1e-10
+    assert np.array_equal(ocg.psi_t.entanglementEntropy(first=1, count=2), S[1:3])

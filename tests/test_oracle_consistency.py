@@ -226,3 +226,22 @@ def test_observables_restatement_on_exact_states():
     got2 = obs.expectation_values(psi, n * (n - 1))
     want2 = [float(sum(abs(vec[c]) ** 2 * c[j] * (c[j] - 1) for c in confs)) for j in range(L)]
     assert np.allclose(got2, want2, atol=1e-12)
+
+
+def test_entropy_restatement_on_exact_states():
+    """oracle.observables.entanglement_entropy against the Schmidt spectrum of the dense state vector."""
+    import itertools
+    from oracle import bh_mps as ob, observables as obs
+    L, D, Np = 4, 3, 4
+    rng = np.random.default_rng(11)
+    vec = np.zeros((D,) * L, dtype=complex)
+    for c in itertools.product(range(D), repeat=L):
+        if sum(c) == Np:
+            vec[c] = rng.normal() + 1j * rng.normal()
+    vec /= np.linalg.norm(vec)
+    psi = ob.mps_from_statevector(vec.reshape(-1), L, D)
+    got = obs.entanglement_entropy(psi)
+    for i in range(1, L):
+        p = np.linalg.svd(vec.reshape(D ** i, D ** (L - i)), compute_uv=False) ** 2
+        p = p[p > 1e-12]
+        assert abs(got[i - 1] + (p * np.log(p)).sum()) < 1e-12
