@@ -1535,6 +1535,25 @@ int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* x
   if (nchains < 1) nchains = 1;
   nchains = std::min(nchains, std::max(nrows, 1));
   CK(cudaSetDevice(st->ctx->dev));
+  {
+    // rows in flight are also bounded by memory: a chain owns two work states, the 2*chi product state of K|psi> with its
+    // workspace, and the chunk store of propagated slices (about 1 GB at chi=100, 17 GB at chi=256)
+    Layout l1, l2;
+    l1.init(st->L, st->D, st->cap);
+    l2.init(st->L, st->D, st->cap, 2);
+    int chunk_est = 32;
+    if (const char* e = getenv("OCMPS_HESSIAN_CHUNK")) chunk_est = std::max(1, atoi(e));
+    const double nD2 = (double)l2.cap * st->D;
+    const double per_chain = 16.0 * ((chunk_est + 6.0) * (double)l1.total + 2.0 * (double)l2.total + 2.0 * nD2 * nD2 +
+                                     8.0 * nD2 * l2.cap);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && per_chain > 0.0) {
+      int have = 0;                                        // chains of this shape that already own their buffers
+      for (Workspace* w : st->ctx->pool) if (w->L == st->L && w->D == st->D && w->cap == st->cap && w->rowstore) ++have;
+      const int fit = have + (int)std::min<double>(1e6, 0.8 * (double)free_b / per_chain);
+      nchains = std::max(1, std::min(nchains, fit));
+    }
+  }
   std::vector<Workspace*> wss(nchains);
   std::vector<ocmps_mps*> psiH(nchains, nullptr);
   for (int c = 0; c < nchains; ++c) {
