@@ -138,3 +138,19 @@ def test_gloo_world_size_2_row_gather(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_site_operator_diagonals_and_queue_default():
+    """Host-side pieces of the observables: the operator diagonals are those of include/BH_sites.h:129-171 (N: n,
+    N(N-1): n^2 - n, NN: n^2), and importing the package asks for one hardware queue per chain stream unless the user
+    has chosen a value."""
+    import os
+    import numpy as np
+    import optimalcontrolmps_b200 as oc
+    n = np.arange(6.0)
+    ops = oc.SliceStore.SITE_OPS
+    assert np.array_equal(ops["N"](n), n)
+    assert np.array_equal(ops["N(N-1)"](n), n * n - n)
+    assert np.array_equal(ops["NN"](n), n * n)
+    assert np.array_equal(ops["Id"](n), np.ones(6))
+    assert os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS") is not None
