@@ -309,3 +309,38 @@ def test_entanglement_entropy_on_resident_slices(golden):
         want = obs.entanglement_entropy(to_oracle(ocg.psi_t.get(i).download()))
         assert np.max(np.abs(S[i] - want)) < 1e-10
     assert np.array_equal(ocg.psi_t.entanglementEntropy(first=1, count=2), S[1:3])
+
+
+def test_reference_costtests_goldens_on_the_gpu():
+    """The golden fidelities and costs the reference's own tests hold (tests/CostTests.cpp:67-133, 136-203: L=5, Npart=5,
+    d=5, U 2 -> 50, T=0.1, tstep=0.01, M=5, Cutoff 1e-8) evaluated by the GPU engine.  Tolerance 1e-5: the reference's
+    numbers come from inexact DMRG ground states (visible at t=0); ours from exact diagonalisation."""
+    import optimalcontrolmps_b200 as oc
+    from oracle import ground_state as og
+    FID_LIN = [0.214338, 0.214325, 0.215126, 0.217281, 0.221019, 0.22621, 0.232328, 0.238484, 0.243617, 0.246862, 0.24801]
+    FID_ONE = [0.214338, 0.214233, 0.213919, 0.213398, 0.212672, 0.211744, 0.210618, 0.2093, 0.207796, 0.206112, 0.204256]
+    FID_GRP = [0.214338, 0.21411, 0.216706, 0.222581, 0.229759, 0.23623, 0.242512, 0.249913, 0.256515, 0.259334, 0.259687]
+    TOL = 1e-5
+    L, Npart, d = 5, 5, 5
+    J, cs, ce, T, ts, M = 1.0, 2.0, 50.0, 0.1, 1e-2, 5
+    N = int(T / ts + 1)
+    psi_i = og.ground_state_ed(L, d + 1, Npart, J, cs)
+    psi_f = og.ground_state_ed(L, d + 1, Npart, J, ce)
+    st = make_stepper(oc, L, d, J, ts, 1e-8, None)
+    grape = oc.OptimalControl(to_host(psi_f), to_host(psi_i), st, N, 0.0)
+    u = oc.SeedGenerator.linspace(cs, ce, N)
+    assert abs(grape.getCost(u) - 0.375995) < TOL                                        # :78
+    assert np.max(np.abs(np.array(grape.getFidelityForAllT(u, False)) - FID_LIN)) < TOL  # :75
+    assert abs(grape.getCost([1.0] * N) - 0.397872) < TOL                                # :93
+    assert np.max(np.abs(np.array(grape.getFidelityForAllT([1.0] * N, False)) - FID_ONE)) < TOL
+    basis = oc.ControlBasisFactory.buildChoppedSineBasis(oc.SeedGenerator.linspace(cs, ce, N), ts, T, M)
+    group = oc.OptimalControl(to_host(psi_f), to_host(psi_i), st, basis, 0.0)
+    assert abs(group.getCost([0.0] * M) - 0.375995) < TOL                                # :112
+    assert np.max(np.abs(np.array(group.getFidelityForAllT([0.0] * M, False)) - FID_LIN)) < TOL
+    c2 = oc.SeedGenerator.linspace(0, 7, M)
+    assert abs(group.getCost(c2) - 0.370157) < TOL                                       # :127
+    assert np.max(np.abs(np.array(group.getFidelityForAllT(c2, False)) - FID_GRP)) < TOL
+    grape.setGamma(1)                                                                    # :136-203
+    assert abs(grape.getCost(oc.SeedGenerator.linspace(cs, ce, N)) - 11520.4) < 1e-1
+    group.setGamma(1)
+    assert abs(group.getCost(c2) - 48360.2) < 1e-1
