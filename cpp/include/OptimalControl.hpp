@@ -42,6 +42,12 @@ class OptimalControl {
   stdvec calcFidelityForAllT(const stdvec& control, const bool new_control = true);
 
  public:
+  // psi_t / xi_t / xiHlist live in device stores owned by this object; a copy would have to duplicate gigabytes of
+  // slices to keep the reference's value semantics (every copy of the reference's class is deep), so copies are
+  // disabled instead of silently aliasing the caches of two objects.  Moves are fine.
+  OptimalControl(const OptimalControl&) = delete;
+  OptimalControl& operator=(const OptimalControl&) = delete;
+  OptimalControl(OptimalControl&&) = default;
   // GRAPE constructor
   OptimalControl(IQMPS& psi_target, IQMPS& psi_init, TimeStepper& timeStepper, size_t N, double gamma, bool BFGS = false);
   // GROUP constructor

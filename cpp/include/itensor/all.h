@@ -95,6 +95,12 @@ class IQMPO {
  public:
   enum Kind { None, PropagatorDerivative };
   Kind kind = None;
+  // the stepper that built this MPO (BH_tDMRG::propagatorDeriv): keeps its device gates alive and lets
+  // exactApplyMPO(stepper.propagatorDeriv(u), psi, stepper.getArgs()) find the matching engine object directly
+  std::shared_ptr<void> owner;
+  ocmps_stepper* stepper = nullptr;
+  double cutoff = -1.0;
+  int maxm = 0;
   IQMPO() {}
   explicit IQMPO(Kind k) : kind(k) {}
 };

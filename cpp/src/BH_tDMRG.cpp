@@ -8,10 +8,13 @@
 #include <mutex>
 
 namespace {
-// exactApplyMPO(K, psi, args) carries no stepper in its signature; steppers register by (Cutoff, Maxm) so that the
-// call site src/OptimalControl.cpp:256 -- exactApplyMPO(stepper.propagatorDeriv(u), psi, stepper.getArgs()) -- resolves.
+// exactApplyMPO(K, psi, args) carries no stepper in its signature.  The MPO returned by propagatorDeriv names the stepper
+// that built it (the reference's call site is exactApplyMPO(stepper.propagatorDeriv(u), psi, stepper.getArgs()),
+// src/OptimalControl.cpp:256); an MPO without one falls back to the live steppers registered here, matched on the full
+// shape (L, D, capacity) and Args.  Entries are weak: a destroyed stepper can never be handed out.
+struct RegEntry { int L, D, cap; double cutoff; int maxm; std::weak_ptr<void> owner; ocmps_stepper* h; };
 std::mutex g_reg_mutex;
-std::vector<std::pair<std::pair<double, int>, ocmps_stepper*>> g_registry;
+std::vector<RegEntry> g_registry;
 }  // namespace
 
 BH_tDMRG::BH_tDMRG(const SiteSet& sites, const double J, const double tstep, const Args& args, int chi_cap)
@@ -25,7 +28,9 @@ BH_tDMRG::BH_tDMRG(const SiteSet& sites, const double J, const double tstep, con
   cap_ = (int)std::min<long long>(chi_cap, full);
   ocmps_check(ocmps_stepper_create(default_context(), L, D, J, tstep, cutoff, maxm, cap_, 0, &p_->h), "ocmps_stepper_create");
   std::lock_guard<std::mutex> lock(g_reg_mutex);
-  g_registry.push_back({{cutoff, maxm}, p_->h});
+  g_registry.erase(std::remove_if(g_registry.begin(), g_registry.end(), [](const RegEntry& e) { return e.owner.expired(); }),
+                   g_registry.end());
+  g_registry.push_back({L, D, cap_, cutoff, maxm, std::weak_ptr<void>(p_), p_->h});
 }
 
 void BH_tDMRG::setTstep(const double t) {
@@ -37,7 +42,14 @@ double BH_tDMRG::getTstep() const { return tstep_; }
 
 Args BH_tDMRG::getArgs() const { return args_; }
 
-IQMPO BH_tDMRG::propagatorDeriv(const double&) const { return IQMPO(IQMPO::PropagatorDerivative); }   // constant, argument unused
+IQMPO BH_tDMRG::propagatorDeriv(const double&) const {      // constant, argument unused (src/BH_tDMRG.cpp:238-241)
+  IQMPO K(IQMPO::PropagatorDerivative);
+  K.owner = p_;
+  K.stepper = p_ ? p_->h : nullptr;
+  K.cutoff = args_.defined("Cutoff") ? args_.getReal("Cutoff") : -1.0;
+  K.maxm = args_.defined("Maxm") ? args_.getInt("Maxm") : 0;
+  return K;
+}
 
 void BH_tDMRG::step(IQMPS& psi, const double from, const double to, bool propagateForward) const {
   if (psi.capacity() != cap_) psi = psi.withCapacity(cap_);
@@ -50,12 +62,19 @@ IQMPS exactApplyMPO(const IQMPO& K, const IQMPS& psi, const Args& args) {
   const double cutoff = args.defined("Cutoff") ? args.getReal("Cutoff") : -1.0;
   const int maxm = args.defined("Maxm") ? args.getInt("Maxm") : 0;
   ocmps_stepper* st = nullptr;
-  {
+  std::shared_ptr<void> keep;                   // holds the stepper alive for the duration of the call
+  if (K.stepper && K.owner && K.cutoff == cutoff && K.maxm == maxm) {
+    st = K.stepper;
+    keep = K.owner;
+  } else {
     std::lock_guard<std::mutex> lock(g_reg_mutex);
-    for (auto it = g_registry.rbegin(); it != g_registry.rend(); ++it)
-      if (it->first.first == cutoff && it->first.second == maxm) { st = it->second; break; }
+    for (auto it = g_registry.rbegin(); it != g_registry.rend(); ++it) {
+      if (it->L != psi.N() || it->D != psi.D() || it->cap != psi.capacity() || it->cutoff != cutoff || it->maxm != maxm) continue;
+      keep = it->owner.lock();
+      if (keep) { st = it->h; break; }
+    }
   }
-  if (!st) throw std::invalid_argument("exactApplyMPO: no BH_tDMRG with these Args exists");
+  if (!st) throw std::invalid_argument("exactApplyMPO: no live BH_tDMRG with this shape (L, D, capacity) and these Args exists");
   IQMPS out(psi.N(), psi.D(), psi.capacity());
   ocmps_check(ocmps_apply_K(st, psi.handle(), out.handle()), "ocmps_apply_K");
   return out;

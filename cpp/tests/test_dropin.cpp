@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <thread>
 #include <vector>
 
 #include "BH_nlp.hpp"
@@ -99,6 +100,33 @@ int main(int argc, char** argv) {
     bool sok = (int)SvN.size() == L - 1;
     for (double x : SvN) sok = sok && x > -1e-12 && x < std::log((double)cap) + 1e-9;
     check(sok, "entanglementEntropy: L-1 values within [0, ln chi]", SvN.empty() ? 0.0 : SvN[SvN.size() / 2]);
+  }
+  {   // re-entrancy: two std::threads step two states on ONE const stepper (src/OptimalControl.cpp:424-430,
+      // src/BH_tDMRG.cpp:113-115) and two OptimalControl objects are evaluated concurrently (tests/GradientTests.cpp:261-285)
+    const BH_tDMRG& cst = stepper;
+    auto run = [&](IQMPS& s, bool fwd) { for (int k = 0; k + 1 < std::min(N, 6); ++k) cst.step(s, fwd ? u[k] : u[N - 1 - k], fwd ? u[k + 1] : u[N - 2 - k], fwd); };
+    IQMPS a_seq = psi_i, b_seq = psi_f, a_par = psi_i, b_par = psi_f;
+    run(a_seq, true);
+    run(b_seq, false);
+    std::thread t1([&] { run(a_par, true); }), t2([&] { run(b_par, false); });
+    t1.join(); t2.join();
+    const double da = std::abs(overlapC(a_seq, a_par)) - 1.0, db = std::abs(overlapC(b_seq, b_par)) - 1.0;
+    check(std::fabs(da) < 1e-11 && std::fabs(db) < 1e-11 && a_seq.bondDims() == a_par.bondDims() && b_seq.bondDims() == b_par.bondDims(),
+          "two threads on one const stepper = sequential", std::max(std::fabs(da), std::fabs(db)));
+    OptimalControl<BH_tDMRG> P1(psi_f, psi_i, stepper, (size_t)N, gamma), P2(psi_f, psi_i, stepper, (size_t)N, gamma);
+    std::vector<double> ua(u), ub(u);
+    for (size_t i = 0; i < ub.size(); ++i) ub[i] += 0.01 * (double)(i % 3);
+    const double c1 = P1.getCost(ua), c2 = P2.getCost(ub);
+    double p1 = 0, p2 = 0;
+    std::thread t3([&] { p1 = P1.getCost(ua); }), t4([&] { p2 = P2.getCost(ub); });
+    t3.join(); t4.join();
+    check(std::fabs(p1 - c1) < 1e-11 && std::fabs(p2 - c2) < 1e-11, "concurrent getCost on two problems = sequential", std::max(std::fabs(p1 - c1), std::fabs(p2 - c2)));
+  }
+  {   // a temporary stepper that has been destroyed must never be handed to exactApplyMPO (registry of live steppers)
+    { BH_tDMRG tmp(sites, J, tstep, {"Cutoff=", cutoff, "Maxm=", maxm > 0 ? maxm : cap}, cap); (void)tmp; }
+    IQMPS k0 = exactApplyMPO(IQMPO(IQMPO::PropagatorDerivative), psi, stepper.getArgs());     // MPO without an owner: registry lookup
+    IQMPS k1 = exactApplyMPO(stepper.propagatorDeriv(u[0]), psi, stepper.getArgs());
+    check(std::fabs(std::abs(overlapC(k0, k1)) - norm(k0) * norm(k1)) < 1e-10 * norm(k0) * norm(k1), "exactApplyMPO resolves the live stepper", norm(k0));
   }
   IQMPS kpsi = exactApplyMPO(stepper.propagatorDeriv(u[0]), psi, stepper.getArgs());
   const Cplx k1 = overlapC(psi, kpsi), k2 = overlapC(psi, stepper.propagatorDeriv(u[0]), psi);

@@ -501,6 +501,8 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   __shared__ double s_rdr[JAC_NV_SMEM], s_rdi[JAC_NV_SMEM];   // diagonal of R
   __shared__ short s_perm[JAC_NV_SMEM], s_permA[JAC_NV_SMEM], s_permB[JAC_NV_SMEM];
   const DecompWork* w = b.dw;
+  // the grid is sized from the largest charge seen at upload time: a block table that outgrew it must not go unnoticed
+  if (blockIdx.x == 0 && threadIdx.x == 0 && w->nblocks > (int)gridDim.x) atomicOr(b.status, OCMPS_ST_TOOMANYBLK);
   if ((int)blockIdx.x >= w->nblocks) return;
   const DecompBlock B = w->blk[blockIdx.x];
   const int nv = B.nv, len = B.len, ld = w->ld, mode = w->mode;
@@ -1418,6 +1420,7 @@ void launch_decomp_setup(const DecompArgs& a, const DecompBuffers& b, cudaStream
 }
 
 #include <vector>
+#include <mutex>
 static bool g_prof_on = false;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 static size_t g_prof_used = 0;
@@ -1460,12 +1463,16 @@ void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_
   struct Tail { cudaEvent_t e; cudaStream_t s; ~Tail() { if (e) cudaEventRecord(e, s); } } tail{e1, s};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 64 && !g_jac_attr_set[dev]) {
+  static std::mutex attr_mu;
+  if (dev < 64) {
+  std::lock_guard<std::mutex> attr_lock(attr_mu);
+  if (!g_jac_attr_set[dev]) {
     cudaFuncSetAttribute(jacobi_blocks_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(jacobi_blocks_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(build_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cudaFuncSetAttribute(jacobi_rot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(JAC_BLOCKED_ROWS * 16 * JAC_EPL * sizeof(cplx)));
     g_jac_attr_set[dev] = true;
+  }
   }
   jacobi_blocks_kernel<true, true><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
   if (long_rows) jacobi_blocks_kernel<true, false><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);

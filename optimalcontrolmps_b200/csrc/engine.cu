@@ -76,10 +76,15 @@ struct Layout {
 
 struct ocmps_ctx {
   int dev = 0;
-  int* d_status = nullptr;
   cudaStream_t stream0 = nullptr;
-  int qmax = 0;                 // largest boson-number label uploaded so far: bounds the number of charge blocks
+  // Everything below is shared by concurrent C-ABI calls (the reference steps one const BH_tDMRG from several
+  // std::threads, src/OptimalControl.cpp:424-430) and guarded by `mu`.  A call checks workspaces out of the pool for its
+  // duration (WsLease); a workspace -- stream, scratch buffers, step graphs, device status word -- is never shared
+  // by two calls in flight.
+  std::mutex mu;
+  std::atomic<int> qmax{0};     // largest boson-number label uploaded so far: bounds the number of charge blocks
   std::vector<struct Workspace*> pool;
+  std::vector<long long> dead_mps;   // serials of destroyed MPS: their step graphs are dropped when a workspace is next leased
 };
 
 struct ocmps_mps {
@@ -90,6 +95,7 @@ struct ocmps_mps {
   int* d_dims = nullptr;
   int* d_q = nullptr;       // (L+1) x cap
   int llim = 0, rlim = 2;
+  long long serial = 0;     // unique id: key of the step graphs captured for this MPS (an address can be reused, a serial cannot)
   cplx* site(int j) const { return arena[cur[j]] + lay.offs.o[j]; }
   cplx* other(int j) const { return arena[1 - cur[j]] + lay.offs.o[j]; }
   int* dim(int b) const { return d_dims + b; }
@@ -123,6 +129,10 @@ struct Op {
 struct Workspace {
   ocmps_ctx* ctx = nullptr;
   int L = 0, D = 0, cap = 0;
+  bool busy = false;           // checked out by a call in flight (guarded by ctx->mu)
+  size_t dead_seen = 0;        // prefix of ctx->dead_mps whose graphs have been dropped here
+  int* d_status = nullptr;     // device status word of this workspace (kernels OR error bits into it)
+  cplx* d_div = nullptr; int div_cap = 0;      // divT accumulator of the BFGS branch
   cudaStream_t stream = nullptr;
   cplx* theta = nullptr;
   cplx* cbuf = nullptr;
@@ -147,11 +157,13 @@ struct Workspace {
   Workspace* bigws = nullptr;  // decomposition buffers for 2*cap
   double* d_norm = nullptr;    // scalar outputs
   StepParams* d_params = nullptr;   // per-step scalars and pointers (device), see StepParams
+  ocmps_mps* tmpK = nullptr;        // K|xi_i> before it goes to its slot (ocmps_store_apply_K)
   ocmps_mps* psiH = nullptr;        // Hessian-row state of this chain
   ocmps_store* rowstore = nullptr;  // Hessian rows: the last few propagated slices, overlapped with xiH in one batched pass
-  // CUDA graphs of one Trotter step (+ slice store), keyed by stepper serial, MPS buffers, buffer parity, with/without store
+  // CUDA graphs of one Trotter step (+ slice store), keyed by stepper serial, MPS serial, buffer parity, with/without
+  // store, and the block-grid bound (ctx->qmax) that the launches of the captured sequence were sized with
   struct StepGraph { cudaGraphExec_t exec = nullptr; unsigned long long flips = 0; int launches = 0; int seen = 0; };
-  std::map<std::tuple<long long, const void*, unsigned long long, int>, StepGraph> graphs;
+  std::map<std::tuple<long long, long long, unsigned long long, int, int>, StepGraph> graphs;
 };
 
 struct ocmps_stepper {
@@ -189,15 +201,20 @@ int alloc_mps(ocmps_ctx* ctx, int L, int D, int cap, ocmps_mps** out, int mult =
   CK(cudaMemset(m->d_dims, 0, sizeof(int) * (L + 1)));
   CK(cudaMemset(m->d_q, 0, sizeof(int) * (size_t)(L + 1) * cap));
   for (int j = 0; j < L; ++j) m->cur[j] = 0;
+  { static std::atomic<long long> next_serial{1}; m->serial = next_serial++; }
   // the memsets above run on the legacy default stream, which does not order against the engine's non-blocking
   // streams: make sure they have landed before any chain touches the new buffers
-  CK(cudaDeviceSynchronize());
+  CK(cudaStreamSynchronize(cudaStreamLegacy));
   *out = m;
   return OCMPS_OK;
 }
 
 void free_mps(ocmps_mps* m) {
   if (!m) return;
+  if (m->ctx) {      // step graphs captured for this MPS hold its buffer addresses: have every workspace drop them
+    std::lock_guard<std::mutex> lock(m->ctx->mu);
+    m->ctx->dead_mps.push_back(m->serial);
+  }
   cudaFree(m->arena[0]); cudaFree(m->arena[1]); cudaFree(m->d_dims); cudaFree(m->d_q);
   delete m;
 }
@@ -225,7 +242,9 @@ int alloc_ws(ocmps_ctx* ctx, int L, int D, int cap, bool with_work, Workspace** 
   CK(cudaMalloc(&w->db.partial, sizeof(double) * 64));
   CK(cudaMalloc(&w->d_norm, sizeof(double) * 4));
   CK(cudaMalloc(&w->d_params, sizeof(StepParams)));
-  w->db.status = ctx->d_status;
+  CK(cudaMalloc(&w->d_status, sizeof(int)));
+  CK(cudaMemset(w->d_status, 0, sizeof(int)));
+  w->db.status = w->d_status;
   w->db2 = w->db;                                     // shares status, partial; everything a decomposition writes is separate
   CK(cudaMalloc(&w->db2.dw, sizeof(DecompWork)));
   CK(cudaMalloc(&w->db2.vec_idx, sizeof(int) * 3 * NV_MAX));
@@ -272,49 +291,94 @@ void free_ws(Workspace* w) {
   if (w->ev_trunc) cudaEventDestroy(w->ev_trunc);
   if (w->ev_setup) cudaEventDestroy(w->ev_setup);
   for (auto& kv : w->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (w->psiH) w->psiH->ctx = nullptr;
   free_mps(w->psiH);
+  if (w->tmpK) w->tmpK->ctx = nullptr;
+  free_mps(w->tmpK);
   if (w->rowstore) { cudaFree(w->rowstore->data); cudaFree(w->rowstore->dims); cudaFree(w->rowstore->q); delete w->rowstore; }
   cudaFree(w->E[0]); cudaFree(w->E[1]); cudaFree(w->T); cudaFree(w->odescs); cudaFree(w->d_out);
+  cudaFree(w->d_status); cudaFree(w->d_div);
+  if (w->work) w->work->ctx = nullptr;      // (the context is going away: no graph bookkeeping)
+  if (w->big) w->big->ctx = nullptr;
+  if (w->psiH) w->psiH->ctx = nullptr;
   free_mps(w->work); free_mps(w->big);
   if (w->bigws) free_ws(w->bigws);
   if (w->stream) cudaStreamDestroy(w->stream);
   delete w;
 }
 
-// workspace number `idx` for the given shape (created on demand, owned by the context)
-int get_ws(ocmps_ctx* ctx, int L, int D, int cap, int idx, Workspace** out) {
-  int seen = 0;
-  for (Workspace* w : ctx->pool) {
-    if (w->L == L && w->D == D && w->cap == cap) {
-      if (seen == idx) { *out = w; return OCMPS_OK; }
-      ++seen;
+// Workspaces of one shape checked out of the context's pool for the duration of a C-ABI call.  Two calls in flight
+// (different host threads, different MPS / stores) never share a workspace, so `step`, the sweeps and the overlaps are
+// re-entrant on one const stepper like the reference's (src/BH_tDMRG.cpp:113-115).  The lowest-numbered free workspaces
+// are taken first: a single-threaded caller always gets the same ones back, with their step graphs and Hessian buffers.
+struct WsLease {
+  ocmps_ctx* ctx = nullptr;
+  std::vector<Workspace*> ws;
+  WsLease() = default;
+  WsLease(const WsLease&) = delete;
+  WsLease& operator=(const WsLease&) = delete;
+  ~WsLease() { release(); }
+  void release() {
+    if (!ctx || ws.empty()) return;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    for (Workspace* w : ws) w->busy = false;
+    ws.clear();
+  }
+  int acquire(ocmps_ctx* c, int L, int D, int cap, int n) {
+    ctx = c;
+    std::lock_guard<std::mutex> lock(c->mu);
+    for (Workspace* w : c->pool) {
+      if ((int)ws.size() == n) break;
+      if (!w->busy && w->L == L && w->D == D && w->cap == cap) { w->busy = true; ws.push_back(w); }
     }
+    while ((int)ws.size() < n) {
+      Workspace* w = nullptr;
+      int rc = alloc_ws(c, L, D, cap, true, &w);
+      if (rc) return rc;
+      w->busy = true;
+      c->pool.push_back(w);
+      ws.push_back(w);
+    }
+    for (Workspace* w : ws) {          // graphs of MPS destroyed since this workspace was last used
+      if (w->dead_seen == c->dead_mps.size()) continue;
+      if (!w->graphs.empty()) {
+        std::vector<long long> dead(c->dead_mps.begin() + w->dead_seen, c->dead_mps.end());
+        std::sort(dead.begin(), dead.end());
+        for (auto it = w->graphs.begin(); it != w->graphs.end();) {
+          if (std::binary_search(dead.begin(), dead.end(), std::get<1>(it->first))) {
+            if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
+            it = w->graphs.erase(it);
+          } else {
+            ++it;
+          }
+        }
+      }
+      w->dead_seen = c->dead_mps.size();
+    }
+    return OCMPS_OK;
   }
-  while (seen <= idx) {
-    Workspace* w = nullptr;
-    int rc = alloc_ws(ctx, L, D, cap, true, &w);
-    if (rc) return rc;
-    ctx->pool.push_back(w);
-    *out = w;
-    ++seen;
+  Workspace* operator[](int i) const { return ws[i]; }
+  // waits for the leased streams and reports (and clears) what the kernels flagged
+  int finish() {
+    int st = 0;
+    for (Workspace* w : ws) {
+      CK(cudaStreamSynchronize(w->stream));
+      int s1 = 0;
+      CK(cudaMemcpy(&s1, w->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+      if (s1) { cudaMemset(w->d_status, 0, sizeof(int)); st |= s1; }
+    }
+    CK(cudaGetLastError());
+    if (st) {
+      std::string msg = "device status:";
+      if (st & OCMPS_ST_CAPACITY) msg += " bond dimension exceeds chi_cap;";
+      if (st & OCMPS_ST_NOCONV) msg += " Jacobi did not converge;";
+      if (st & OCMPS_ST_CHARGE) msg += " charge label >= 256;";
+      if (st & OCMPS_ST_TOOMANYBLK) msg += " more charge blocks than the launch was sized for;";
+      return fail((st & OCMPS_ST_CAPACITY) ? OCMPS_ERR_CAPACITY : OCMPS_ERR_NUMERIC, msg);
+    }
+    return OCMPS_OK;
   }
-  return OCMPS_OK;
-}
-
-int check_status(ocmps_ctx* ctx) {
-  int st = 0;
-  CK(cudaMemcpy(&st, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost));
-  if (st) {
-    cudaMemset(ctx->d_status, 0, sizeof(int));
-    std::string msg = "device status:";
-    if (st & OCMPS_ST_CAPACITY) msg += " bond dimension exceeds chi_cap;";
-    if (st & OCMPS_ST_NOCONV) msg += " Jacobi did not converge;";
-    if (st & OCMPS_ST_CHARGE) msg += " charge label >= 256;";
-    if (st & OCMPS_ST_TOOMANYBLK) msg += " more than 128 charge blocks;";
-    return fail((st & OCMPS_ST_CAPACITY) ? OCMPS_ERR_CAPACITY : OCMPS_ERR_NUMERIC, msg);
-  }
-  return OCMPS_OK;
-}
+};
 
 // ------------------------------------------------------------------------------------------------
 // gates (BondGate) and the op schedule (src/BH_tDMRG.cpp:127-230)
@@ -434,7 +498,7 @@ void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int c
   if (smem < 1024) smem = 1024;
   // blocks are labelled by a charge in [0, qmax + D): launch no more CTAs than that (surplus CTAs would still have to
   // wait for an SM with the full shared-memory carve-out and would serialise concurrent chains)
-  int nblk = std::min(std::min(OCMPS_MAX_BLK, std::max(capV, capC) + a.D), ws->ctx->qmax + a.D + 1);
+  int nblk = std::min(std::min(OCMPS_MAX_BLK, std::max(capV, capC) + a.D), ws->ctx->qmax.load() + a.D + 1);
   const bool need_global = need > JAC_SMEM_LIMIT;    // some block may not fit in shared memory
   // numerical-rank tolerance of the pivoted QR: the neglected weight stays >= 6 orders below the cutoff
   static const double rank_scale = [] { const char* e = getenv("OCMPS_RANK_TOL_SCALE"); return e ? atof(e) : 1e-6; }();
@@ -633,7 +697,7 @@ int step_enqueue(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, double from, do
   if (!graphs_enabled() || profile_is_on()) { body(); return OCMPS_OK; }   // event timing needs plain launches
   unsigned long long parity = 0;
   for (int j = 0; j < lay.L; ++j) parity |= (unsigned long long)(m->cur[j] & 1) << j;
-  auto key = std::make_tuple(st->serial, (const void*)m->arena[0], parity, store ? 1 : 0);
+  auto key = std::make_tuple(st->serial, m->serial, parity, store ? 1 : 0, ws->ctx->qmax.load());
   Workspace::StepGraph& g = ws->graphs[key];
   if (g.exec) {
     for (int j = 0; j < lay.L; ++j) m->cur[j] ^= (int)((g.flips >> j) & 1ull);
@@ -822,7 +886,7 @@ int apply_K_async(ocmps_stepper* st, Workspace* ws, ocmps_mps* in, ocmps_mps* ou
   // compact into the chi_cap layout
   for (int j = 0; j < L; ++j) out->cur[j] = 0;
   copy_bookkeeping_kernel<<<L + 1, 128, 0, s>>>(big->d_dims, big->d_q, lb.cap, out->d_dims, out->d_q, out->lay.cap, L, out->lay.cap,
-                                               st->ctx->d_status);
+                                               ws->d_status);
   launch_pack_copy(big->ptrs(), out->arena[0], out->lay.offs, out->d_dims, L, D, out->lay.max_site_elems, s);
   g_ocmps_launches += 2;
   out->llim = 0; out->rlim = 2;
@@ -857,8 +921,6 @@ int ocmps_ctx_create(int device, ocmps_ctx** out) {
   if (prop.major < 10) return fail(OCMPS_ERR_CUDA, "libocmps is built for sm_100a (Blackwell) only");
   ocmps_ctx* c = new ocmps_ctx();
   c->dev = device;
-  CK(cudaMalloc(&c->d_status, sizeof(int)));
-  CK(cudaMemset(c->d_status, 0, sizeof(int)));
   CK(cudaStreamCreateWithFlags(&c->stream0, cudaStreamNonBlocking));
   *out = c;
   return OCMPS_OK;
@@ -869,16 +931,16 @@ int ocmps_ctx_destroy(ocmps_ctx* ctx) {
   cudaSetDevice(ctx->dev);
   cudaDeviceSynchronize();
   for (Workspace* w : ctx->pool) free_ws(w);
-  cudaFree(ctx->d_status);
   cudaStreamDestroy(ctx->stream0);
   delete ctx;
   return OCMPS_OK;
 }
 
 int ocmps_ctx_synchronize(ocmps_ctx* ctx) {
+  if (!ctx) return fail(OCMPS_ERR_INVALID, "null argument");
   CK(cudaSetDevice(ctx->dev));
-  CK(cudaDeviceSynchronize());
-  return check_status(ctx);
+  CK(cudaDeviceSynchronize());      // every entry point is synchronous, so this only matters next to foreign CUDA work
+  return OCMPS_OK;
 }
 
 // ---- MPS ----
@@ -887,7 +949,7 @@ int ocmps_mps_create(ocmps_ctx* ctx, int L, int D, int chi_cap, ocmps_mps** out)
   return alloc_mps(ctx, L, D, chi_cap, out);
 }
 int ocmps_mps_destroy(ocmps_mps* mps) {
-  if (mps) { cudaSetDevice(mps->ctx->dev); cudaDeviceSynchronize(); free_mps(mps); }
+  if (mps) { cudaSetDevice(mps->ctx->dev); free_mps(mps); }
   return OCMPS_OK;
 }
 
@@ -895,7 +957,6 @@ int ocmps_mps_upload(ocmps_mps* m, const int* bond_dims, const int* charges, con
   if (!m || !bond_dims || !charges || !tensors) return fail(OCMPS_ERR_INVALID, "null argument");
   const Layout& lay = m->lay;
   CK(cudaSetDevice(m->ctx->dev));
-  CK(cudaDeviceSynchronize());
   for (int b = 0; b <= lay.L; ++b)
     if (bond_dims[b] < 1 || bond_dims[b] > lay.capb[b])
       return fail(OCMPS_ERR_CAPACITY, "upload: bond dimension " + std::to_string(bond_dims[b]) + " at bond " + std::to_string(b) +
@@ -913,7 +974,10 @@ int ocmps_mps_upload(ocmps_mps* m, const int* bond_dims, const int* charges, con
       perm[b].resize(nb);
       for (int i = 0; i < nb; ++i) perm[b][i] = i;
       const int* qb = charges + qo;
-      for (int i = 0; i < nb; ++i) m->ctx->qmax = std::max(m->ctx->qmax, qb[i]);
+      for (int i = 0; i < nb; ++i) {
+        int seen = m->ctx->qmax.load();
+        while (qb[i] > seen && !m->ctx->qmax.compare_exchange_weak(seen, qb[i])) {}
+      }
       std::stable_sort(perm[b].begin(), perm[b].end(), [qb](int x, int y) { return qb[x] < qb[y]; });
       std::vector<int> sorted(nb);
       for (int i = 0; i < nb; ++i) sorted[i] = qb[perm[b][i]];
@@ -946,9 +1010,8 @@ int ocmps_mps_upload(ocmps_mps* m, const int* bond_dims, const int* charges, con
 int ocmps_mps_bond_dims(ocmps_mps* m, int* bond_dims) {
   if (!m || !bond_dims) return fail(OCMPS_ERR_INVALID, "null argument");
   CK(cudaSetDevice(m->ctx->dev));
-  CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(bond_dims, m->d_dims, sizeof(int) * (m->lay.L + 1), cudaMemcpyDeviceToHost));
-  return check_status(m->ctx);
+  return OCMPS_OK;
 }
 
 int ocmps_mps_sizes(ocmps_mps* m, long long* n_elems, long long* n_charges) {
@@ -986,10 +1049,13 @@ int ocmps_mps_download(ocmps_mps* m, int* bond_dims, int* charges, double* tenso
 int ocmps_mps_copy(ocmps_mps* dst, ocmps_mps* src) {
   if (!dst || !src) return fail(OCMPS_ERR_INVALID, "null argument");
   CK(cudaSetDevice(src->ctx->dev));
-  CK(cudaDeviceSynchronize());
-  int rc = copy_mps_async(dst, src, src->ctx->stream0);
+  cudaStream_t s = nullptr;                   // a stream of its own: concurrent copies of different MPS do not queue up
+  CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  int rc = copy_mps_async(dst, src, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaStreamDestroy(s);
   if (rc) return rc;
-  CK(cudaStreamSynchronize(src->ctx->stream0));
+  CK(e);
   return OCMPS_OK;
 }
 
@@ -997,31 +1063,29 @@ int ocmps_mps_norm(ocmps_mps* m, double* out) {
   if (!m || !out) return fail(OCMPS_ERR_INVALID, "null argument");
   if (m->llim + 2 != m->rlim) return fail(OCMPS_ERR_INVALID, "norm: MPS has no single orthogonality centre");
   CK(cudaSetDevice(m->ctx->dev));
-  Workspace* ws = nullptr;
-  int rc = get_ws(m->ctx, m->lay.L, m->lay.D, m->lay.cap, 0, &ws);
+  WsLease lease;
+  int rc = lease.acquire(m->ctx, m->lay.L, m->lay.D, m->lay.cap, 1);
   if (rc) return rc;
-  CK(cudaDeviceSynchronize());
+  Workspace* ws = lease[0];
   const int j = m->llim;   // 0-based centre
   launch_norm_only(m->site(j), m->dim(j), m->dim(j + 1), m->lay.D, ws->db.partial, ws->d_norm, 0, ws->stream);
   g_ocmps_launches += 2;
   CK(cudaMemcpyAsync(out, ws->d_norm, sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
-  CK(cudaStreamSynchronize(ws->stream));
-  return OCMPS_OK;
+  return lease.finish();
 }
 
 static int overlap_impl(ocmps_mps* a, ocmps_mps* b, double* re_im, int withK) {
   if (!a || !b || !re_im) return fail(OCMPS_ERR_INVALID, "null argument");
   if (a->lay.L != b->lay.L || a->lay.D != b->lay.D) return fail(OCMPS_ERR_INVALID, "overlap: shape mismatch");
   CK(cudaSetDevice(a->ctx->dev));
-  Workspace* ws = nullptr;
-  int rc = get_ws(a->ctx, a->lay.L, a->lay.D, a->lay.cap, 0, &ws);
+  WsLease lease;
+  int rc = lease.acquire(a->ctx, a->lay.L, a->lay.D, a->lay.cap, 1);
   if (rc) return rc;
-  CK(cudaDeviceSynchronize());
+  Workspace* ws = lease[0];
   rc = overlaps_async(ws, side_of_mps(a), a->lay, side_of_mps(b), b->lay, 1, withK, ws->stream);
   if (rc) return rc;
   CK(cudaMemcpyAsync(re_im, ws->d_out, sizeof(cplx), cudaMemcpyDeviceToHost, ws->stream));
-  CK(cudaStreamSynchronize(ws->stream));
-  return OCMPS_OK;
+  return lease.finish();
 }
 int ocmps_overlap(ocmps_mps* a, ocmps_mps* b, double* re_im) { return overlap_impl(a, b, re_im, 0); }
 int ocmps_overlap_K(ocmps_mps* a, ocmps_mps* b, double* re_im) { return overlap_impl(a, b, re_im, 1); }
@@ -1099,15 +1163,13 @@ int ocmps_step(ocmps_stepper* st, ocmps_mps* psi, double from, double to, int fo
   if (rc) return rc;
   if (psi->llim != 0 || psi->rlim != 2) return fail(OCMPS_ERR_INVALID, "step: orthogonality centre must be at site 1");
   CK(cudaSetDevice(st->ctx->dev));
-  Workspace* ws = nullptr;
-  rc = get_ws(st->ctx, st->L, st->D, st->cap, 0, &ws);
+  WsLease lease;
+  rc = lease.acquire(st->ctx, st->L, st->D, st->cap, 1);
   if (rc) return rc;
-  CK(cudaDeviceSynchronize());
+  Workspace* ws = lease[0];
   rc = step_enqueue(st, psi, ws, from, to, forward != 0, nullptr, 0, ws->stream);
-  if (rc) return rc;
-  CK(cudaStreamSynchronize(ws->stream));
-  CK(cudaGetLastError());
-  return check_status(st->ctx);
+  if (rc) { cudaStreamSynchronize(ws->stream); return rc; }
+  return lease.finish();
 }
 
 int ocmps_debug_jacobi(unsigned long long* out, int reset) { cudaDeviceSynchronize(); debug_jacobi_counters(out, reset != 0); return 0; }
@@ -1115,15 +1177,13 @@ int ocmps_debug_jacobi(unsigned long long* out, int reset) { cudaDeviceSynchroni
 // development aid: run ops [op_begin, op_end) of one step (not part of include/ocmps.h)
 int ocmps_debug_run_ops(ocmps_stepper* st, ocmps_mps* psi, double from, double to, int forward, int op_begin, int op_end) {
   CK(cudaSetDevice(st->ctx->dev));
-  Workspace* ws = nullptr;
-  int rc = get_ws(st->ctx, st->L, st->D, st->cap, 0, &ws);
+  WsLease lease;
+  int rc = lease.acquire(st->ctx, st->L, st->D, st->cap, 1);
   if (rc) return rc;
-  CK(cudaDeviceSynchronize());
+  Workspace* ws = lease[0];
   { StepParams hp; fill_step_params(st, from, to, forward != 0, nullptr, 0, hp); launch_set_step_params(hp, ws->d_params, ws->stream); }
   run_step_body(st, psi, ws, ws->stream, op_begin, op_end);
-  CK(cudaStreamSynchronize(ws->stream));
-  CK(cudaGetLastError());
-  return check_status(st->ctx);
+  return lease.finish();
 }
 
 int ocmps_apply_K(ocmps_stepper* st, ocmps_mps* in, ocmps_mps* out) {
@@ -1133,15 +1193,13 @@ int ocmps_apply_K(ocmps_stepper* st, ocmps_mps* in, ocmps_mps* out) {
   rc = check_shapes(st, out->lay, "apply_K");
   if (rc) return rc;
   CK(cudaSetDevice(st->ctx->dev));
-  Workspace* ws = nullptr;
-  rc = get_ws(st->ctx, st->L, st->D, st->cap, 0, &ws);
+  WsLease lease;
+  rc = lease.acquire(st->ctx, st->L, st->D, st->cap, 1);
   if (rc) return rc;
-  CK(cudaDeviceSynchronize());
+  Workspace* ws = lease[0];
   rc = apply_K_async(st, ws, in, out, ws->stream);
-  if (rc) return rc;
-  CK(cudaStreamSynchronize(ws->stream));
-  CK(cudaGetLastError());
-  return check_status(st->ctx);
+  if (rc) { cudaStreamSynchronize(ws->stream); return rc; }
+  return lease.finish();
 }
 
 // ---- stores ----
@@ -1156,7 +1214,7 @@ int ocmps_store_create(ocmps_ctx* ctx, int L, int D, int chi_cap, int nslots, oc
   CK(cudaMalloc(&s->dims, sizeof(int) * (size_t)(L + 1) * nslots));
   CK(cudaMalloc(&s->q, sizeof(int) * (size_t)(L + 1) * chi_cap * nslots));
   CK(cudaMemset(s->dims, 0, sizeof(int) * (size_t)(L + 1) * nslots));
-  CK(cudaDeviceSynchronize());
+  CK(cudaStreamSynchronize(cudaStreamLegacy));
   *out = s;
   return OCMPS_OK;
 }
@@ -1171,7 +1229,6 @@ int ocmps_store_destroy(ocmps_store* s) {
 int ocmps_store_get(ocmps_store* store, int slot, ocmps_mps* out) {
   if (!store || !out) return fail(OCMPS_ERR_INVALID, "null argument");
   CK(cudaSetDevice(store->ctx->dev));
-  CK(cudaDeviceSynchronize());
   int rc = store_get_async(store, slot, out, store->ctx->stream0);
   if (rc) return rc;
   CK(cudaStreamSynchronize(store->ctx->stream0));
@@ -1180,7 +1237,6 @@ int ocmps_store_get(ocmps_store* store, int slot, ocmps_mps* out) {
 int ocmps_store_put(ocmps_store* store, int slot, ocmps_mps* in) {
   if (!store || !in) return fail(OCMPS_ERR_INVALID, "null argument");
   CK(cudaSetDevice(store->ctx->dev));
-  CK(cudaDeviceSynchronize());
   int rc = store_put_async(store, slot, in, store->ctx->stream0);
   if (rc) return rc;
   CK(cudaStreamSynchronize(store->ctx->stream0));
@@ -1189,7 +1245,6 @@ int ocmps_store_put(ocmps_store* store, int slot, ocmps_mps* in) {
 int ocmps_store_bond_dims(ocmps_store* store, int* out) {
   if (!store || !out) return fail(OCMPS_ERR_INVALID, "null argument");
   CK(cudaSetDevice(store->ctx->dev));
-  CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out, store->dims, sizeof(int) * (size_t)(store->lay.L + 1) * store->nslots, cudaMemcpyDeviceToHost));
   return OCMPS_OK;
 }
@@ -1221,19 +1276,15 @@ int ocmps_forward_sweep(ocmps_stepper* st, ocmps_mps* psi_init, const double* u,
   if (rc) return rc;
   if (!store) return fail(OCMPS_ERR_INVALID, "null store");
   CK(cudaSetDevice(st->ctx->dev));
-  Workspace* ws = nullptr;
-  rc = get_ws(st->ctx, st->L, st->D, st->cap, 0, &ws);
+  WsLease lease;
+  rc = lease.acquire(st->ctx, st->L, st->D, st->cap, 1);
   if (rc) return rc;
-  CK(cudaDeviceSynchronize());
+  Workspace* ws = lease[0];
   rc = sweep_enqueue_init(st, ws, psi_init, store, 0);
-  if (rc) return rc;
-  for (int i = 0; i < Nt - 1; ++i) {
+  for (int i = 0; i < Nt - 1 && !rc; ++i)
     rc = step_enqueue(st, ws->work, ws, u[i], u[i + 1], true, store, i + 1, ws->stream);
-    if (rc) return rc;
-  }
-  CK(cudaStreamSynchronize(ws->stream));
-  CK(cudaGetLastError());
-  return check_status(st->ctx);
+  if (rc) { cudaStreamSynchronize(ws->stream); return rc; }
+  return lease.finish();
 }
 
 int ocmps_backward_sweep(ocmps_stepper* st, ocmps_mps* psi_target, const double* u, int Nt, ocmps_store* store) {
@@ -1241,19 +1292,15 @@ int ocmps_backward_sweep(ocmps_stepper* st, ocmps_mps* psi_target, const double*
   if (rc) return rc;
   if (!store) return fail(OCMPS_ERR_INVALID, "null store");
   CK(cudaSetDevice(st->ctx->dev));
-  Workspace* ws = nullptr;
-  rc = get_ws(st->ctx, st->L, st->D, st->cap, 1, &ws);
+  WsLease lease;
+  rc = lease.acquire(st->ctx, st->L, st->D, st->cap, 1);
   if (rc) return rc;
-  CK(cudaDeviceSynchronize());
+  Workspace* ws = lease[0];
   rc = sweep_enqueue_init(st, ws, psi_target, store, Nt - 1);
-  if (rc) return rc;
-  for (int i = Nt - 1; i > 0; --i) {
+  for (int i = Nt - 1; i > 0 && !rc; --i)
     rc = step_enqueue(st, ws->work, ws, u[i], u[i - 1], false, store, i - 1, ws->stream);
-    if (rc) return rc;
-  }
-  CK(cudaStreamSynchronize(ws->stream));
-  CK(cudaGetLastError());
-  return check_status(st->ctx);
+  if (rc) { cudaStreamSynchronize(ws->stream); return rc; }
+  return lease.finish();
 }
 
 int ocmps_sweep_pair(ocmps_stepper* st, ocmps_mps* psi_init, ocmps_mps* psi_target, const double* u, int Nt, ocmps_store* psi_store,
@@ -1264,27 +1311,20 @@ int ocmps_sweep_pair(ocmps_stepper* st, ocmps_mps* psi_init, ocmps_mps* psi_targ
   if (rc) return rc;
   if (!psi_store || !xi_store) return fail(OCMPS_ERR_INVALID, "null store");
   CK(cudaSetDevice(st->ctx->dev));
-  Workspace *wa = nullptr, *wb = nullptr;
-  rc = get_ws(st->ctx, st->L, st->D, st->cap, 0, &wa);
+  WsLease lease;
+  rc = lease.acquire(st->ctx, st->L, st->D, st->cap, 2);
   if (rc) return rc;
-  rc = get_ws(st->ctx, st->L, st->D, st->cap, 1, &wb);
-  if (rc) return rc;
-  CK(cudaDeviceSynchronize());
+  Workspace *wa = lease[0], *wb = lease[1];
   rc = sweep_enqueue_init(st, wa, psi_init, psi_store, 0);
-  if (rc) return rc;
-  rc = sweep_enqueue_init(st, wb, psi_target, xi_store, Nt - 1);
-  if (rc) return rc;
-  for (int k = 0; k < Nt - 1; ++k) {      // interleave the two chains so both streams stay fed
+  if (!rc) rc = sweep_enqueue_init(st, wb, psi_target, xi_store, Nt - 1);
+  for (int k = 0; k < Nt - 1 && !rc; ++k) {      // interleave the two chains so both streams stay fed
     rc = step_enqueue(st, wa->work, wa, u[k], u[k + 1], true, psi_store, k + 1, wa->stream);
-    if (rc) return rc;
+    if (rc) break;
     const int i = Nt - 1 - k;
     rc = step_enqueue(st, wb->work, wb, u[i], u[i - 1], false, xi_store, i - 1, wb->stream);
-    if (rc) return rc;
   }
-  CK(cudaStreamSynchronize(wa->stream));
-  CK(cudaStreamSynchronize(wb->stream));
-  CK(cudaGetLastError());
-  return check_status(st->ctx);
+  if (rc) { cudaStreamSynchronize(wa->stream); cudaStreamSynchronize(wb->stream); return rc; }
+  return lease.finish();
 }
 
 int ocmps_sweep_batch(ocmps_stepper* st, int nchains, ocmps_mps** starts, const int* forward, const double* u, int Nt,
@@ -1297,17 +1337,13 @@ int ocmps_sweep_batch(ocmps_stepper* st, int nchains, ocmps_mps** starts, const 
     if (!stores[c]) return fail(OCMPS_ERR_INVALID, "null store");
   }
   CK(cudaSetDevice(st->ctx->dev));
-  std::vector<Workspace*> wss(nchains);
-  for (int c = 0; c < nchains; ++c) {
-    rc = get_ws(st->ctx, st->L, st->D, st->cap, c, &wss[c]);
-    if (rc) return rc;
-  }
-  CK(cudaDeviceSynchronize());
-  for (int c = 0; c < nchains; ++c) {
+  WsLease lease;
+  rc = lease.acquire(st->ctx, st->L, st->D, st->cap, nchains);
+  if (rc) return rc;
+  const std::vector<Workspace*>& wss = lease.ws;
+  for (int c = 0; c < nchains && !rc; ++c)
     rc = sweep_enqueue_init(st, wss[c], starts[c], stores[c], forward[c] ? 0 : Nt - 1);
-    if (rc) return rc;
-  }
-  for (int k = 0; k < Nt - 1; ++k) {          // all chains advance in lock step so every stream stays fed
+  for (int k = 0; k < Nt - 1 && !rc; ++k) {          // all chains advance in lock step so every stream stays fed
     for (int c = 0; c < nchains; ++c) {
       const double* uc = u + (size_t)c * Nt;
       Workspace* ws = wss[c];
@@ -1317,12 +1353,11 @@ int ocmps_sweep_batch(ocmps_stepper* st, int nchains, ocmps_mps** starts, const 
         const int i = Nt - 1 - k;
         rc = step_enqueue(st, ws->work, ws, uc[i], uc[i - 1], false, stores[c], i - 1, ws->stream);
       }
-      if (rc) return rc;
+      if (rc) break;
     }
   }
-  CK(cudaDeviceSynchronize());
-  CK(cudaGetLastError());
-  return check_status(st->ctx);
+  if (rc) { for (Workspace* w : wss) cudaStreamSynchronize(w->stream); return rc; }
+  return lease.finish();
 }
 
 int ocmps_backward_sweep_divT(ocmps_stepper* st, ocmps_mps* psi_target, const double* u, int Nt, ocmps_store* psi_store,
@@ -1331,35 +1366,40 @@ int ocmps_backward_sweep_divT(ocmps_stepper* st, ocmps_mps* psi_target, const do
   if (rc) return rc;
   if (!psi_store || !divT) return fail(OCMPS_ERR_INVALID, "null argument");
   CK(cudaSetDevice(st->ctx->dev));
-  Workspace* ws = nullptr;
-  rc = get_ws(st->ctx, st->L, st->D, st->cap, 1, &ws);
+  WsLease lease;
+  rc = lease.acquire(st->ctx, st->L, st->D, st->cap, 1);
   if (rc) return rc;
-  CK(cudaDeviceSynchronize());
-  rc = sweep_enqueue_init(st, ws, psi_target, nullptr, 0);
-  if (rc) return rc;
-  cplx* d_div = nullptr;
-  CK(cudaMalloc(&d_div, sizeof(cplx) * Nt));
-  for (int i = Nt - 1; i >= 0; --i) {
-    rc = overlaps_async(ws, side_of_mps(ws->work), ws->work->lay, side_of_store(psi_store, i), psi_store->lay, 1, 1, ws->stream);
-    if (rc) { cudaFree(d_div); return rc; }
-    CK(cudaMemcpyAsync(d_div + i, ws->d_out, sizeof(cplx), cudaMemcpyDeviceToDevice, ws->stream));
-    if (i > 0) { rc = step_enqueue(st, ws->work, ws, u[i], u[i - 1], false, nullptr, 0, ws->stream); if (rc) { cudaFree(d_div); return rc; } }
+  Workspace* ws = lease[0];
+  if (ws->div_cap < Nt) {                       // kept with the workspace: no allocation per call
+    CK(cudaStreamSynchronize(ws->stream));
+    cudaFree(ws->d_div); ws->d_div = nullptr; ws->div_cap = 0;
+    CK(cudaMalloc(&ws->d_div, sizeof(cplx) * Nt));
+    ws->div_cap = Nt;
   }
-  CK(cudaMemcpyAsync(divT, d_div, sizeof(cplx) * Nt, cudaMemcpyDeviceToHost, ws->stream));
-  CK(cudaStreamSynchronize(ws->stream));
-  cudaFree(d_div);
-  CK(cudaGetLastError());
-  return check_status(st->ctx);
+  cplx* d_div = ws->d_div;
+  rc = sweep_enqueue_init(st, ws, psi_target, nullptr, 0);
+  for (int i = Nt - 1; i >= 0 && !rc; --i) {
+    rc = overlaps_async(ws, side_of_mps(ws->work), ws->work->lay, side_of_store(psi_store, i), psi_store->lay, 1, 1, ws->stream);
+    if (rc) break;
+    if (cudaMemcpyAsync(d_div + i, ws->d_out, sizeof(cplx), cudaMemcpyDeviceToDevice, ws->stream) != cudaSuccess) {
+      rc = fail(OCMPS_ERR_CUDA, "cudaMemcpyAsync failed"); break;
+    }
+    if (i > 0) rc = step_enqueue(st, ws->work, ws, u[i], u[i - 1], false, nullptr, 0, ws->stream);
+  }
+  if (!rc && cudaMemcpyAsync(divT, d_div, sizeof(cplx) * Nt, cudaMemcpyDeviceToHost, ws->stream) != cudaSuccess)
+    rc = fail(OCMPS_ERR_CUDA, "cudaMemcpyAsync failed");
+  if (rc) { cudaStreamSynchronize(ws->stream); return rc; }
+  return lease.finish();
 }
 
 static int store_overlaps_impl(ocmps_store* bra_store, ocmps_mps* bra, ocmps_store* ket, int Nt, int withK, double* out) {
   if (!ket || !out || Nt < 1 || Nt > ket->nslots) return fail(OCMPS_ERR_INVALID, "bad argument");
   ocmps_ctx* ctx = ket->ctx;
   CK(cudaSetDevice(ctx->dev));
-  Workspace* ws = nullptr;
-  int rc = get_ws(ctx, ket->lay.L, ket->lay.D, ket->lay.cap, 0, &ws);
+  WsLease lease;
+  int rc = lease.acquire(ctx, ket->lay.L, ket->lay.D, ket->lay.cap, 1);
   if (rc) return rc;
-  CK(cudaDeviceSynchronize());
+  Workspace* ws = lease[0];
   const int chunk = 64;
   for (int z0 = 0; z0 < Nt; z0 += chunk) {
     const int nb = std::min(chunk, Nt - z0);
@@ -1395,10 +1435,10 @@ int ocmps_store_site_expectations(ocmps_store* store, int first, int count, cons
   const Layout& lay = store->lay;
   const int L = lay.L, D = lay.D, nk = nops + 1;
   CK(cudaSetDevice(ctx->dev));
-  Workspace* ws = nullptr;
-  int rc = get_ws(ctx, L, D, lay.cap, 0, &ws);
+  WsLease lease;
+  int rc = lease.acquire(ctx, L, D, lay.cap, 1);
   if (rc) return rc;
-  CK(cudaDeviceSynchronize());
+  Workspace* ws = lease[0];
   std::vector<double> h_ops((size_t)nk * D);
   for (int s = 0; s < D; ++s) h_ops[s] = 1.0;                               // slot 0: identity
   for (int k = 0; k < nops; ++k)
@@ -1455,10 +1495,10 @@ int ocmps_store_entanglement_entropy(ocmps_store* store, int first, int count, d
   const int L = lay.L, D = lay.D;
   if (L < 2) return fail(OCMPS_ERR_INVALID, "entanglement_entropy needs L >= 2");
   CK(cudaSetDevice(ctx->dev));
-  Workspace* ws = nullptr;
-  int rc = get_ws(ctx, L, D, lay.cap, 0, &ws);
+  WsLease lease;
+  int rc = lease.acquire(ctx, L, D, lay.cap, 1);
   if (rc) return rc;
-  CK(cudaDeviceSynchronize());
+  Workspace* ws = lease[0];
   double* d_out = nullptr;
   CK(cudaMalloc(&d_out, sizeof(double) * (size_t)count * (L - 1)));
   cudaStream_t s = ws->stream;
@@ -1490,8 +1530,7 @@ int ocmps_store_entanglement_entropy(ocmps_store* store, int first, int count, d
   cudaStreamSynchronize(s);
   cudaFree(d_out);
   if (rc) return rc;
-  CK(cudaGetLastError());
-  return check_status(ctx);
+  return lease.finish();
 }
 
 int ocmps_store_apply_K(ocmps_stepper* st, ocmps_store* in, int Nt, ocmps_store* out) {
@@ -1502,27 +1541,24 @@ int ocmps_store_apply_K(ocmps_stepper* st, ocmps_store* in, int Nt, ocmps_store*
   if (rc) return rc;
   CK(cudaSetDevice(st->ctx->dev));
   const int nch = std::min(Nt, 8);
-  std::vector<Workspace*> wss(nch);
-  std::vector<ocmps_mps*> tmp(nch, nullptr);
-  for (int c = 0; c < nch; ++c) {
-    rc = get_ws(st->ctx, st->L, st->D, st->cap, c, &wss[c]);
-    if (rc) return rc;
-    rc = alloc_mps(st->ctx, st->L, st->D, st->cap, &tmp[c]);
-    if (rc) return rc;
-  }
-  CK(cudaDeviceSynchronize());
+  WsLease lease;
+  rc = lease.acquire(st->ctx, st->L, st->D, st->cap, nch);
+  if (rc) return rc;
+  const std::vector<Workspace*>& wss = lease.ws;
+  for (int c = 0; c < nch; ++c)
+    if (!wss[c]->tmpK) {          // kept with the workspace: no allocation per call
+      rc = alloc_mps(st->ctx, st->L, st->D, st->cap, &wss[c]->tmpK);
+      if (rc) return rc;
+    }
   for (int i = 0; i < Nt; ++i) {
     Workspace* ws = wss[i % nch];
     rc = store_get_async(in, i, ws->work, ws->stream);
-    if (!rc) rc = apply_K_async(st, ws, ws->work, tmp[i % nch], ws->stream);
-    if (!rc) rc = store_put_async(out, i, tmp[i % nch], ws->stream);
+    if (!rc) rc = apply_K_async(st, ws, ws->work, ws->tmpK, ws->stream);
+    if (!rc) rc = store_put_async(out, i, ws->tmpK, ws->stream);
     if (rc) break;
   }
-  CK(cudaDeviceSynchronize());
-  for (int c = 0; c < nch; ++c) free_mps(tmp[c]);
-  if (rc) return rc;
-  CK(cudaGetLastError());
-  return check_status(st->ctx);
+  if (rc) { for (Workspace* w : wss) cudaStreamSynchronize(w->stream); return rc; }
+  return lease.finish();
 }
 
 int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* xiH_store, const double* u, int Nt, const int* rows,
@@ -1549,16 +1585,21 @@ int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* x
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && per_chain > 0.0) {
       int have = 0;                                        // chains of this shape that already own their buffers
-      for (Workspace* w : st->ctx->pool) if (w->L == st->L && w->D == st->D && w->cap == st->cap && w->rowstore) ++have;
+      {
+        std::lock_guard<std::mutex> lock(st->ctx->mu);
+        for (Workspace* w : st->ctx->pool)
+          if (!w->busy && w->L == st->L && w->D == st->D && w->cap == st->cap && w->rowstore) ++have;
+      }
       const int fit = have + (int)std::min<double>(1e6, 0.8 * (double)free_b / per_chain);
       nchains = std::max(1, std::min(nchains, fit));
     }
   }
-  std::vector<Workspace*> wss(nchains);
+  WsLease lease;
+  rc = lease.acquire(st->ctx, st->L, st->D, st->cap, nchains);
+  if (rc) return rc;
+  const std::vector<Workspace*>& wss = lease.ws;
   std::vector<ocmps_mps*> psiH(nchains, nullptr);
   for (int c = 0; c < nchains; ++c) {
-    rc = get_ws(st->ctx, st->L, st->D, st->cap, c, &wss[c]);
-    if (rc) return rc;
     if (!wss[c]->psiH) {          // kept with the workspace so that its step graphs stay valid across calls
       rc = alloc_mps(st->ctx, st->L, st->D, st->cap, &wss[c]->psiH);
       if (rc) return rc;
@@ -1574,7 +1615,7 @@ int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* x
   for (int c = 0; c < nchains; ++c) {
     Workspace* ws = wss[c];
     if (ws->rowstore && ws->rowstore->nslots != chunk) {
-      cudaDeviceSynchronize();
+      cudaStreamSynchronize(ws->stream);
       cudaFree(ws->rowstore->data); cudaFree(ws->rowstore->dims); cudaFree(ws->rowstore->q); delete ws->rowstore;
       ws->rowstore = nullptr;
     }
@@ -1589,7 +1630,7 @@ int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* x
   CK(cudaMalloc(&d_norms, sizeof(double) * Nt));
   CK(cudaMemset(d_ovl, 0, sizeof(cplx) * (size_t)Nt * Nt));
   CK(cudaMemset(d_norms, 0, sizeof(double) * Nt));
-  CK(cudaDeviceSynchronize());
+  CK(cudaStreamSynchronize(cudaStreamLegacy));
   // longest rows first, dealt round-robin to the chains.  Host threads (the reference's work-queue threads,
   // src/OptimalControl.cpp:305-335) each drive a subset of the chains; a thread advances its chains in lock step so
   // that all of its streams stay fed.
@@ -1671,15 +1712,14 @@ int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* x
   }
   rc = err_rc;
   if (rc) g_err = err_msg;
-  cudaDeviceSynchronize();
+  for (Workspace* w : wss) cudaStreamSynchronize(w->stream);
   if (!rc) {
     cudaMemcpy(ovl, d_ovl, sizeof(cplx) * (size_t)Nt * Nt, cudaMemcpyDeviceToHost);
     cudaMemcpy(norms, d_norms, sizeof(double) * Nt, cudaMemcpyDeviceToHost);
   }
   cudaFree(d_ovl); cudaFree(d_norms);
   if (rc) return rc;
-  CK(cudaGetLastError());
-  return check_status(st->ctx);
+  return lease.finish();
 }
 
 }  // extern "C"
