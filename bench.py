@@ -39,6 +39,31 @@ def nt():
     return int(CFG["T"] / CFG["tstep"] + 1)
 
 
+def config_dict():
+    """The `config` object of the JSON line -- identical in both arms."""
+    return {"workload": "cfg2: BH L=20 Npart=20 d=5 T=2.0 tstep=0.01 GROUP M=10 chi=100, one cost+gradient evaluation "
+                        "(getAnalyticGradient(c,true) + getCost(c,false)) per step; N>1: one independent evaluation per GPU",
+            **CFG, "Nt": nt(), "l2": "inputs larger than L2: the two slice stores are rewritten every evaluation (5.7 GB capacity)"}
+
+
+HESS_M = 20      # cfg3: GROUP basis of the Hessian workload (tests/HessianTests.cpp:212 range for the coefficients)
+
+
+def make_hessian_problem_host(seed=0):
+    """cfg3 (BASELINE.json configs[2]): the cfg2 chain with a GROUP basis of M=20 chopped sines, c ~ U(-2,2)^20."""
+    import optimalcontrolmps_b200 as oc
+    rng = np.random.default_rng(3000 + seed)
+    u0 = oc.SeedGenerator.linsigmoidSeed(CFG["U_i"], CFG["U_f"], nt(), np.random.default_rng(7))
+    basis = oc.ControlBasisFactory.buildChoppedSineBasis(u0, CFG["tstep"], CFG["T"], HESS_M)
+    c = np.array(oc.SeedGenerator.randomCoeffSeed(-2.0, 2.0, HESS_M, rng))
+    for _ in range(40):
+        u = np.array(basis.convertControl(list(c)))
+        if u.min() >= 2.0 and u.max() <= 100.0:
+            break
+        c *= 0.8
+    return basis, c
+
+
 def make_problem_host(seed):
     """Basis and coefficient vector of the synthetic control for `seed` (pure host math, shared by both arms)."""
     import optimalcontrolmps_b200 as oc
@@ -194,11 +219,19 @@ def run_reference(args):
     sample = (f"oracle port (NumPy/OpenBLAS, {ncores} threads): step 1 = one complete cost+gradient evaluation ({full:.1f} s); "
               f"steps 2..K = 1 forward + 1 backward Trotter step + 1 MPO overlap from each of 8 evenly spaced slices of that "
               f"evaluation, extrapolated to 2*(Nt-1) steps + Nt+1 overlaps")
+    note = ("NumPy/OpenBLAS port of the reference's algorithm (the ITensor build cannot be produced here): interpreter- and "
+            "small-LAPACK-bound, not core-bound -- `cores` is the host's core count, the BLAS thread pool is nominal; a "
+            "block-sparse C++ ITensor build would be faster than this port.  One CPU process: compare with the GPU arm at N=1 only.")
+    # Hessian on the CPU, estimated (a full one is ~20 000 Trotter steps): row steps at the mean forward-step time of this run
+    hess_est = None
+    if "fwd_step_s" in det:
+        hess_est = (N - 2) * (N - 1) / 2.0 * det["fwd_step_s"] + 2 * (N - 1) * det["fwd_step_s"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_eval * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "complex128 (f64)", "data": "synthetic",
-            "config": {"workload": "cfg2: BH L=20 Npart=20 d=5 T=2.0 tstep=0.01 GROUP M=10 chi=100 single cost+gradient eval", **CFG},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample, **det},
+            "config": config_dict(),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample, "note": note,
+                             "hessian_wall_s_estimate": hess_est, **det},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
             "result": {"cost": float(cost), "grad_norm": float(np.linalg.norm(grad)),
                        "max_bond_dim": int(max(max(p.bond_dims()) for p in ocp.psi_t))}}
@@ -274,18 +307,19 @@ def run_ours(args):
         dist.barrier()
     torch.cuda.synchronize()
     l0 = lib.ocmps_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import ctypes
     t0 = time.perf_counter()
-    e0.record()
+    lib.ocmps_timer_start(ctx.h)                  # CUDA events on the library's own stream (torch's stream sees none of this work)
     res = None
     for _ in range(args.steps):
         res = one_eval()
-    e1.record()
+    dev_ms_c = ctypes.c_double()
+    lib.ocmps_timer_stop(ctx.h, ctypes.byref(dev_ms_c))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - t0
-    dev_ms = e0.elapsed_time(e1)
+    dev_ms = dev_ms_c.value
     launches = lib.ocmps_launch_count() - l0
     sampler.stop_flag = True
     if rank == 0:
@@ -306,8 +340,10 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "complex128 (f64)", "data": "synthetic",
-            "config": {"workload": "cfg2: BH L=20 Npart=20 d=5 T=2.0 tstep=0.01 GROUP M=10 chi=100 single cost+gradient eval per GPU (N>1: independent replicas, one all-gather of the results)",
-                       **CFG, "Nt": N, "l2": "inputs larger than L2: the two slice stores are rewritten every eval (5.7 GB capacity)"},
+            "config": config_dict(),
+            "timing": "value: CUDA events recorded on the library's own stream around the timed region (every C-ABI call is synchronous, so "
+                      "the events bracket all device work of the evaluations); e2e: host wall clock around the same calls made through "
+                      "the public API with host control / gradient buffers",
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(8 * M + 8 * N), "d2h_bytes_per_step": int(8 * (1 + M) + 16 * 2 * N)},
             "gpu_launches": int(launches), "clocks": sampler.summary(),
             "result": {"cost": float(allres[0][0]), "grad_norm": float(np.linalg.norm(allres[0][1:])),
@@ -330,7 +366,11 @@ def run_ours(args):
             except Exception:
                 traffic = None
         ach = fl_blk / (ms_tot * 1e-3) / 1e12 if ms_tot > 0 else 0.0
-        line["roofline"] = {"kernel": "jacobi_blocks_kernel + jacobi_rot_kernel (pivoted QR + block Jacobi SVD of every charge block)", "bound": "tensor",
+        line["roofline"] = {"kernel": "jacobi_blocks_kernel + jacobi_rot_kernel (pivoted QR + block Jacobi SVD of every charge block)",
+                            "bound": "latency",
+                            "bound_note": "FP64 DFMA kernels (no tensor-core instruction) bound by instruction issue and dependent chains of the "
+                                          "sequential Householder steps / rotation rounds on one SM per charge block; the FP64 GEMM peak is the "
+                                          "denominator SURVEY.md 8d asks for, not a bound these kernels can approach",
                             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
                             "traffic": traffic, "launches": int(nl), "avg_launch_us": ms_tot * 1e3 / max(nl, 1),
                             "share_of_two_stream_time": ms_tot / (2.0 * t_dev / args.steps * 1e3),
@@ -353,10 +393,10 @@ def run_ours(args):
         if args.batch > 1 and world == 1:
             line["batched"] = batched_bench(args.batch, oc, st, psi_i, psi_f, ocp, c)
         if args.hessian_nt:
-            line["hessian"] = hessian_bench(args.hessian_nt, oc, ocd, st, psi_i, psi_f, world, dev, torch)
+            line["hessian"] = hessian_bench(args.hessian_nt, oc, ocd, st, psi_i, psi_f, world, rank, dev, torch)
         print(json.dumps(line), flush=True)
     elif args.hessian_nt:
-        hessian_bench(args.hessian_nt, oc, ocd, st, psi_i, psi_f, world, dev, torch)
+        hessian_bench(args.hessian_nt, oc, ocd, st, psi_i, psi_f, world, rank, dev, torch)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -381,32 +421,63 @@ def batched_bench(B, oc, st, psi_i, psi_f, ocp0, c0):
             "max_abs_diff_vs_single": float(max(abs(res[0][0] - c1), np.max(np.abs(np.array(res[0][1]) - np.array(g1)))))}
 
 
-def hessian_bench(Nt, oc, ocd, st, psi_i, psi_f, world, dev, torch):
-    """GRAPE Hessian of a horizon of Nt points with rows sharded over the ranks (cfg3 shape when Nt=201)."""
+def hessian_bench(Nt, oc, ocd, st, psi_i, psi_f, world, rank, dev, torch):
+    """cfg3 (BASELINE.json configs[2]): full GROUP Hessian (M=20) of the cfg2 chain through the public API -- getHessian on one
+    GPU, distributed.sharded_hessian (rows dealt to the ranks, one NCCL all-gather) on N.  Strong scaling: the work is fixed.
+    On N>1 rank 0 first times the same Hessian alone on its GPU (the other ranks wait), so that the line carries its own
+    1-GPU reference and the strong-scaling efficiency t1 / (N * tN)."""
     import torch.distributed as dist
-    u = list(np.linspace(CFG["U_i"], 30.0, Nt))
-    och = oc.OptimalControl(psi_f, psi_i, st, Nt, CFG["gamma"])
+    basis, c = make_hessian_problem_host(0)
+    if Nt != nt():                       # reduced horizon (development): GRAPE on a ramp of Nt points
+        basis = None
+    och = oc.OptimalControl(psi_f, psi_i, st, basis if basis is not None else Nt, CFG["gamma"])
     och.setThreadCount(4)
+    ctrl = list(c) if basis is not None else list(np.linspace(CFG["U_i"], 30.0, Nt))
 
-    def once():
+    def once(sharded):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        if world > 1:
-            H = ocd.sharded_hessian(och, u, True, dev)
+        if sharded:
+            H = ocd.sharded_hessian(och, ctrl, True, dev, convert=True)
         else:
-            H = np.array(och.getHessian(u, True))
+            H = np.array(och.getHessian(ctrl, True))
         torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
         if world > 1:
-            dist.barrier()
-        return time.perf_counter() - t0, H
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt[0])
+        return dt, H
 
+    out = {"workload": f"cfg3: full GROUP Hessian M={HESS_M if basis is not None else 0} (Nt={Nt}, {Nt - 2} rows, "
+                       f"{(Nt - 2) * (Nt - 1) // 2} row steps + both sweeps + K.xi), BH L=20 chi=100", "Nt": Nt, "n_gpus": world,
+           "scaling": "strong"}
+    t1 = None
+    if world > 1:
+        # 1-GPU reference inside the same run (rank 0 alone; first call allocates and captures, second call is timed)
+        if rank == 0:
+            och.getHessian(ctrl, True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            H1 = np.array(och.getHessian(ctrl, True))
+            torch.cuda.synchronize()
+            t1 = time.perf_counter() - t0
+            out["t1_wall_s"] = t1
+            out["t1_checksum"] = float(np.abs(H1).sum())
+        dist.barrier()
     # first call: allocates the per-row workspaces and captures their step graphs; second call: what every further
     # Hessian of an optimisation run costs
-    cold, _ = once()
-    warm, H = once()
-    return {"Nt": Nt, "wall_s": warm, "first_call_s": cold, "n_gpus": world, "checksum": float(np.abs(H).sum())}
+    cold, _ = once(world > 1)
+    warm, H = once(world > 1)
+    out.update({"wall_s": warm, "first_call_s": cold, "checksum": float(np.abs(H).sum()), "shape": list(H.shape)})
+    if world > 1 and t1 is not None:
+        out["efficiency"] = t1 / (world * warm)
+        out["max_abs_diff_vs_1gpu"] = float(np.max(np.abs(H - H1)))
+    elif world == 1:
+        out["efficiency"] = 1.0
+    return out
 
 
 def main():
@@ -415,7 +486,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--hessian-nt", type=int, default=0, help="additionally time a sharded GRAPE Hessian with this many time points")
+    ap.add_argument("--hessian-nt", type=int, default=201,
+                    help="time points of the Hessian block (201 = cfg3, the full GROUP M=20 Hessian; 0 switches the block off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0, help="seed of the synthetic control")
     ap.add_argument("--distinct-seeds", action="store_true", help="N>1: rank r evaluates the control of seed r")

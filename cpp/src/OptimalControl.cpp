@@ -162,20 +162,23 @@ template <class TS> stdvec OptimalControl<TS>::calcAnalyticGradient(const stdvec
 // ---- Hessian (:252-372) ----
 template <class TS> rowmat OptimalControl<TS>::calcHessian(const stdvec& u, const bool new_control) {
   if (BFGS) throw std::logic_error("getHessian is undefined in BFGS mode");
-  if (new_control) { calculatedXi = false; calcPsiXiDivT(u); }
-  if (!calculatedXi) { calcXi(u); calcDivT(u); }
+  // prerequisites (:284-303) and rows (:305-335) as one event-ordered schedule on the GPU; the cache flags end up as the
+  // reference leaves them
+  const bool do_psi = new_control, do_xi = new_control || !calculatedXi;
   rowmat H = calcRegularizationHessian(u);
-  const Cplx of = overlapFactor();
   if (!xiHlist) xiHlist = newStore();
-  ocmps_check(ocmps_store_apply_K(timeStepper.handle(), xi_t->h, (int)N, xiHlist->h), "ocmps_store_apply_K");   // :300-303
   std::vector<int> rows;
   for (size_t r = 1; r + 1 < N; ++r) rows.push_back((int)r);
   std::vector<Cplx> ovl(N * N, Cplx(0.0, 0.0));
   std::vector<double> norms(N, 0.0);
+  fidOvl.assign(N, Cplx(0.0, 0.0));
   const int chains = (int)std::max<size_t>(1, std::min<size_t>(48, 12 * threadCount));   // rows in flight; measured optimum at chi=100
-  if (!rows.empty())
-    ocmps_check(ocmps_hessian_rows(timeStepper.handle(), psi_t->h, xiHlist->h, u.data(), (int)N, rows.data(), (int)rows.size(), chains,
-                                   reinterpret_cast<double*>(ovl.data()), norms.data()), "ocmps_hessian_rows");
+  ocmps_check(ocmps_hessian_eval(timeStepper.handle(), psi_init.handle(), psi_target.handle(), u.data(), (int)N, psi_t->h, xi_t->h,
+                                 xiHlist->h, rows.data(), (int)rows.size(), chains, do_psi ? 1 : 0, do_xi ? 1 : 0,
+                                 reinterpret_cast<double*>(divT.data()), reinterpret_cast<double*>(fidOvl.data()),
+                                 reinterpret_cast<double*>(ovl.data()), norms.data()), "ocmps_hessian_eval");
+  calculatedXi = true;
+  const Cplx of = std::conj(fidOvl[N - 1]);                                                                   // :297
   const double ts2 = tstep * tstep;
   for (int r : rows) {
     H[r][r] += ts2 * ((of * ovl[r * N + r]).real() - (divT[r] * std::conj(divT[r])).real());                  // :260-264

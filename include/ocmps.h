@@ -52,6 +52,9 @@ int ocmps_profile_read(double* out4);
 int ocmps_ctx_create(int device, ocmps_ctx** out);
 int ocmps_ctx_destroy(ocmps_ctx* ctx);
 int ocmps_ctx_synchronize(ocmps_ctx* ctx);
+/* measurement aid (bench.py): a pair of CUDA events on the library's own stream; stop returns the milliseconds between them */
+int ocmps_timer_start(ocmps_ctx* ctx);
+int ocmps_timer_stop(ocmps_ctx* ctx, double* ms);
 
 /* ---- MPS container (itensor::IQMPS in the reference's signatures) ---- */
 int ocmps_mps_create(ocmps_ctx* ctx, int L, int D, int chi_cap, ocmps_mps** out);
@@ -130,6 +133,17 @@ int ocmps_store_apply_K(ocmps_stepper* st, ocmps_store* in, int Nt, ocmps_store*
  * the caller assembles H (it also needs divT and the regularisation).  `nchains` independent rows are in flight at once. */
 int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* xiH_store, const double* u, int Nt,
                        const int* rows, int nrows, int nchains, double* ovl /* 2*Nt*Nt */, double* norms /* Nt */);
+
+/* calcHessian_parallel (src/OptimalControl.cpp:282-338) as ONE schedule: the prerequisites of :284-303 -- psi sweep (do_psi),
+ * xi sweep (do_xi), divT, xiHlist_i = exactApplyMPO(K, xi_i) -- and the rows of :305-335 are enqueued together and ordered by
+ * events: row r starts as soon as psi_r exists, K.xi follows the xi sweep slice by slice, and a row's overlaps with xiHlist wait
+ * for that store without stalling the row.  do_psi / do_xi = 0 reuse the slices already in psi_store / xi_store (the
+ * new_control = false and calculatedXi cases of :284-294).  Outputs: divT[i] = <xi_i|K|psi_i>, fid[i] = <target|psi_i>
+ * (overlapFactor :297 is conj(fid[Nt-1])), and ovl / norms as in ocmps_hessian_rows. */
+int ocmps_hessian_eval(ocmps_stepper* st, ocmps_mps* psi_init, ocmps_mps* psi_target, const double* u, int Nt,
+                       ocmps_store* psi_store, ocmps_store* xi_store, ocmps_store* xiH_store, const int* rows, int nrows,
+                       int nchains, int do_psi, int do_xi, double* divT /* 2*Nt */, double* fid /* 2*Nt */,
+                       double* ovl /* 2*Nt*Nt */, double* norms /* Nt */);
 
 #ifdef __cplusplus
 }

@@ -14,14 +14,14 @@ LIB_PATH = os.path.join(_HERE, "libocmps.so")
 # every symbol include/ocmps.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "ocmps_last_error", "ocmps_version", "ocmps_launch_count", "ocmps_profile_enable", "ocmps_profile_read",
-    "ocmps_ctx_create", "ocmps_ctx_destroy", "ocmps_ctx_synchronize",
+    "ocmps_ctx_create", "ocmps_ctx_destroy", "ocmps_ctx_synchronize", "ocmps_timer_start", "ocmps_timer_stop",
     "ocmps_mps_create", "ocmps_mps_destroy", "ocmps_mps_upload", "ocmps_mps_sizes", "ocmps_mps_download",
     "ocmps_mps_bond_dims", "ocmps_mps_copy", "ocmps_mps_norm", "ocmps_overlap", "ocmps_overlap_K",
     "ocmps_stepper_create", "ocmps_stepper_destroy", "ocmps_stepper_set_tstep", "ocmps_stepper_get_tstep",
     "ocmps_step", "ocmps_apply_K", "ocmps_stepper_schedule", "ocmps_stepper_gate",
     "ocmps_store_create", "ocmps_store_destroy", "ocmps_store_get", "ocmps_store_put", "ocmps_store_bond_dims",
     "ocmps_forward_sweep", "ocmps_backward_sweep", "ocmps_sweep_pair", "ocmps_sweep_batch", "ocmps_backward_sweep_divT",
-    "ocmps_store_overlaps", "ocmps_store_divT", "ocmps_store_apply_K", "ocmps_hessian_rows",
+    "ocmps_store_overlaps", "ocmps_store_divT", "ocmps_store_apply_K", "ocmps_hessian_rows", "ocmps_hessian_eval",
     "ocmps_store_site_expectations", "ocmps_store_entanglement_entropy",
 ]
 
@@ -53,6 +53,8 @@ def load():
         "ocmps_ctx_create": (i, [i, pvp]),
         "ocmps_ctx_destroy": (i, [vp]),
         "ocmps_ctx_synchronize": (i, [vp]),
+        "ocmps_timer_start": (i, [vp]),
+        "ocmps_timer_stop": (i, [vp, pd]),
         "ocmps_mps_create": (i, [vp, i, i, i, pvp]),
         "ocmps_mps_destroy": (i, [vp]),
         "ocmps_mps_upload": (i, [vp, pi, pi, pd, i, i]),
@@ -85,6 +87,7 @@ def load():
         "ocmps_store_divT": (i, [vp, vp, i, pd]),
         "ocmps_store_apply_K": (i, [vp, vp, i, vp]),
         "ocmps_hessian_rows": (i, [vp, vp, vp, pd, i, pi, i, i, pd, pd]),
+        "ocmps_hessian_eval": (i, [vp, vp, vp, pd, i, vp, vp, vp, pi, i, i, i, i, pd, pd, pd, pd]),
         "ocmps_store_site_expectations": (i, [vp, i, i, pd, i, pd, pd]),
         "ocmps_store_entanglement_entropy": (i, [vp, i, i, pd]),
     }

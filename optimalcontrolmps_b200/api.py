@@ -664,28 +664,31 @@ class OptimalControl:
 
     # -- Hessian (:252-372)
     def _calcHessian(self, control, new_control=True) -> np.ndarray:
+        """calcHessian_parallel (:282-338).  The prerequisites the reference computes one after the other -- psi_t, xi_t
+        and divT if the cache flags ask for them (:284-294), xiHlist (:300-303) -- and the rows (:305-335) go to the GPU as
+        one event-ordered schedule (``ocmps_hessian_eval``); the cache flags end up as the reference leaves them."""
         if self.BFGS:
             raise RuntimeError("getHessian is undefined in BFGS mode (xi_t / xiHlist are not allocated)")
-        if new_control:
-            self.calculatedXi = False
-            self._calcPsiXiDivT(control)
-        if not self.calculatedXi:
-            self._calcXi(control)
-            self._calcDivT()
+        do_psi = bool(new_control)
+        do_xi = bool(new_control) or not self.calculatedXi
         u = self._u(control)
         N = self.N
         H = self._calcRegularizationHessian(control)
-        of = self._overlapFactor()
         if self.xiHlist is None:
             self.xiHlist = self.timeStepper.new_store(N)
-        _lib.check(self.lib.ocmps_store_apply_K(self.timeStepper.h, self.xi_t.h, N, self.xiHlist.h))     # :300-303
         rows = np.array(list(range(1, N - 1)) if self.rows is None else list(self.rows), dtype=np.int32)
         ovl = np.zeros(2 * N * N)
         norms = np.zeros(N)
+        divT = np.zeros(2 * N)
+        fid = np.zeros(2 * N)
         nch = self.hessian_chains or max(1, min(48, 12 * self.threadCount))   # measured (Nt=201, chi=100): 16 -> 25 s, 32 -> 16 s, 48 -> 14 s
-        if rows.size:
-            _lib.check(self.lib.ocmps_hessian_rows(self.timeStepper.h, self.psi_t.h, self.xiHlist.h, _pd(u), N, _pi(rows), rows.size,
-                                                   nch, _pd(ovl), _pd(norms)))
+        _lib.check(self.lib.ocmps_hessian_eval(self.timeStepper.h, self.psi_init.h, self.psi_target.h, _pd(u), N, self.psi_t.h,
+                                               self.xi_t.h, self.xiHlist.h, _pi(rows), rows.size, nch, 1 if do_psi else 0,
+                                               1 if do_xi else 0, _pd(divT), _pd(fid), _pd(ovl), _pd(norms)))
+        self.calculatedXi = True
+        self.divT = divT.view(np.complex128).copy()
+        self._fid_ovl = fid.view(np.complex128).copy()
+        of = complex(np.conj(self._fid_ovl[-1]))                                                            # :297
         ovl = ovl.view(np.complex128).reshape(N, N)
         ts2 = self.tstep * self.tstep
         Hf = np.zeros((N, N))

@@ -85,6 +85,7 @@ struct ocmps_ctx {
   std::atomic<int> qmax{0};     // largest boson-number label uploaded so far: bounds the number of charge blocks
   std::vector<struct Workspace*> pool;
   std::vector<long long> dead_mps;   // serials of destroyed MPS: their step graphs are dropped when a workspace is next leased
+  cudaEvent_t t0 = nullptr, t1 = nullptr;   // ocmps_timer_start / ocmps_timer_stop
 };
 
 struct ocmps_mps {
@@ -134,6 +135,7 @@ struct Workspace {
   int* d_status = nullptr;     // device status word of this workspace (kernels OR error bits into it)
   cplx* d_div = nullptr; int div_cap = 0;      // divT accumulator of the BFGS branch
   cudaStream_t stream = nullptr;
+  cudaStream_t ovl = nullptr;                  // Hessian rows: batched overlaps of finished chunks run beside the chain
   cplx* theta = nullptr;
   cplx* cbuf = nullptr;
   DecompBuffers db;
@@ -304,6 +306,7 @@ void free_ws(Workspace* w) {
   free_mps(w->work); free_mps(w->big);
   if (w->bigws) free_ws(w->bigws);
   if (w->stream) cudaStreamDestroy(w->stream);
+  if (w->ovl) cudaStreamDestroy(w->ovl);
   delete w;
 }
 
@@ -931,8 +934,29 @@ int ocmps_ctx_destroy(ocmps_ctx* ctx) {
   cudaSetDevice(ctx->dev);
   cudaDeviceSynchronize();
   for (Workspace* w : ctx->pool) free_ws(w);
+  if (ctx->t0) { cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1); }
   cudaStreamDestroy(ctx->stream0);
   delete ctx;
+  return OCMPS_OK;
+}
+
+// Device-side stopwatch for bench.py: two CUDA events on the context's own stream.  Every entry point is synchronous, so the
+// stream is idle when either event is recorded and the pair brackets all device work enqueued in between.
+int ocmps_timer_start(ocmps_ctx* ctx) {
+  if (!ctx) return fail(OCMPS_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(ctx->dev));
+  if (!ctx->t0) { CK(cudaEventCreate(&ctx->t0)); CK(cudaEventCreate(&ctx->t1)); }
+  CK(cudaEventRecord(ctx->t0, ctx->stream0));
+  return OCMPS_OK;
+}
+int ocmps_timer_stop(ocmps_ctx* ctx, double* ms) {
+  if (!ctx || !ms || !ctx->t0) return fail(OCMPS_ERR_INVALID, "timer not started");
+  CK(cudaSetDevice(ctx->dev));
+  CK(cudaEventRecord(ctx->t1, ctx->stream0));
+  CK(cudaEventSynchronize(ctx->t1));
+  float f = 0.f;
+  CK(cudaEventElapsedTime(&f, ctx->t0, ctx->t1));
+  *ms = (double)f;
   return OCMPS_OK;
 }
 
@@ -1561,165 +1585,320 @@ int ocmps_store_apply_K(ocmps_stepper* st, ocmps_store* in, int Nt, ocmps_store*
   return lease.finish();
 }
 
-int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* xiH_store, const double* u, int Nt, const int* rows,
-                       int nrows, int nchains, double* ovl, double* norms) {
-  if (!st || !psi_store || !xiH_store || !u || !rows || !ovl || !norms || Nt < 3) return fail(OCMPS_ERR_INVALID, "bad argument");
-  int rc = check_shapes(st, psi_store->lay, "hessian_rows");
+// ------------------------------------------------------------------------------------------------
+// Hessian (src/OptimalControl.cpp:252-372): prerequisites and rows as ONE stream/event schedule
+// ------------------------------------------------------------------------------------------------
+// The reference computes psi_t, xi_t, divT, then xiHlist, then the rows (work queue :305-335).  Row r only needs psi_r to
+// start and the K.xi slices only at its overlaps, so here everything is enqueued at once and ordered by events:
+//   * the psi sweep records an event per stored slice; the chain of row r waits for the event of slice r, i.e. the rows
+//     trail the sweep instead of waiting for it (the sweep is the critical path of a sharded Hessian);
+//   * the xi sweep records an event per slice as well; K|xi_i> (exactApplyMPO :300-303) follows slice by slice on
+//     NK chains;
+//   * a row writes its propagated slices -- starting with K|psi_r> itself, whose overlap is the diagonal entry :260-264 --
+//     into a per-chain ring of NCH chunks; a finished chunk is overlapped with the matching K.xi slices in one batched
+//     transfer-matrix pass on the chain's overlap stream, which also waits for the K.xi store; the row only stalls if
+//     it gets NCH chunks ahead of its overlaps;
+//   * divT and the fidelity overlaps run at the tail of the two sweep streams.
+// With do_psi = do_xi = do_xiH = 0 this is the plain row computation on stores that are already valid.
+static int hessian_run(ocmps_stepper* st, ocmps_mps* psi_init, ocmps_mps* psi_target, const double* u, int Nt, ocmps_store* psi_store,
+                       ocmps_store* xi_store, ocmps_store* xiH_store, const int* rows, int nrows, int nchains, int do_psi, int do_xi,
+                       int do_xiH, double* divT, double* fid, double* ovl, double* norms) {
+  if (!st || !psi_store || !xiH_store || !u || (!rows && nrows > 0) || !ovl || !norms || Nt < 3) return fail(OCMPS_ERR_INVALID, "bad argument");
+  int rc = check_shapes(st, psi_store->lay, "hessian");
   if (rc) return rc;
-  rc = check_shapes(st, xiH_store->lay, "hessian_rows");
+  rc = check_shapes(st, xiH_store->lay, "hessian");
   if (rc) return rc;
+  if (psi_store->nslots < Nt || xiH_store->nslots < Nt) return fail(OCMPS_ERR_INVALID, "hessian: store has fewer slots than Nt");
+  if ((do_xi || do_xiH || divT) && !xi_store) return fail(OCMPS_ERR_INVALID, "hessian: xi store needed");
+  if (xi_store) { rc = check_shapes(st, xi_store->lay, "hessian"); if (rc) return rc; if (xi_store->nslots < Nt) return fail(OCMPS_ERR_INVALID, "hessian: store has fewer slots than Nt"); }
+  if (do_psi) { rc = sweep_args_ok(st, psi_init, u, Nt, psi_store); if (rc) return rc; }
+  if (do_xi) { rc = sweep_args_ok(st, psi_target, u, Nt, xi_store); if (rc) return rc; }
+  if (fid && !psi_target) return fail(OCMPS_ERR_INVALID, "hessian: target state needed for the fidelity overlaps");
+  for (int i = 0; i < nrows; ++i)
+    if (rows[i] < 1 || rows[i] > Nt - 2) return fail(OCMPS_ERR_INVALID, "hessian row out of range [1, Nt-2]");
   if (nchains < 1) nchains = 1;
   nchains = std::min(nchains, std::max(nrows, 1));
   CK(cudaSetDevice(st->ctx->dev));
+  // ring of propagated slices per chain: NCH chunks of CH slots
+  int CH = 32, NCH = 4;
+  if (const char* e = getenv("OCMPS_HESSIAN_CHUNK")) CH = std::max(1, atoi(e));
+  if (const char* e = getenv("OCMPS_HESSIAN_RING")) NCH = std::max(2, atoi(e));
+  CH = std::min(CH, std::max(1, Nt - 1));
+  NCH = std::min(NCH, (Nt - 1 + CH - 1) / CH + 1);
+  if (!do_psi && !do_xiH) NCH = 2;                 // nothing to wait for: double buffering is enough
+  const int ring = CH * NCH;
   {
     // rows in flight are also bounded by memory: a chain owns two work states, the 2*chi product state of K|psi> with its
-    // workspace, and the chunk store of propagated slices (about 1 GB at chi=100, 17 GB at chi=256)
+    // workspace, and the ring of propagated slices (about 2.3 GB at chi=100 with the default ring)
     Layout l1, l2;
     l1.init(st->L, st->D, st->cap);
     l2.init(st->L, st->D, st->cap, 2);
-    int chunk_est = 32;
-    if (const char* e = getenv("OCMPS_HESSIAN_CHUNK")) chunk_est = std::max(1, atoi(e));
     const double nD2 = (double)l2.cap * st->D;
-    const double per_chain = 16.0 * ((chunk_est + 6.0) * (double)l1.total + 2.0 * (double)l2.total + 2.0 * nD2 * nD2 +
-                                     8.0 * nD2 * l2.cap);
+    const double per_chain = 16.0 * ((ring + 6.0) * (double)l1.total + 2.0 * (double)l2.total + 2.0 * nD2 * nD2 + 8.0 * nD2 * l2.cap);
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && per_chain > 0.0) {
       int have = 0;                                        // chains of this shape that already own their buffers
       {
         std::lock_guard<std::mutex> lock(st->ctx->mu);
         for (Workspace* w : st->ctx->pool)
-          if (!w->busy && w->L == st->L && w->D == st->D && w->cap == st->cap && w->rowstore) ++have;
+          if (!w->busy && w->L == st->L && w->D == st->D && w->cap == st->cap && w->rowstore && w->rowstore->nslots == ring) ++have;
       }
       const int fit = have + (int)std::min<double>(1e6, 0.8 * (double)free_b / per_chain);
       nchains = std::max(1, std::min(nchains, fit));
     }
   }
+  const int NK = do_xiH ? std::min(Nt, 8) : 0;
+  // workspaces: [0] psi sweep / fidelity overlaps, [1] xi sweep / divT, [2, 2+NK) K.xi chains, then the row chains.
+  // Always leased in this order so that every role gets the same workspace (and its buffers and graphs) on every call.
   WsLease lease;
-  rc = lease.acquire(st->ctx, st->L, st->D, st->cap, nchains);
+  rc = lease.acquire(st->ctx, st->L, st->D, st->cap, 2 + 8 + nchains);
   if (rc) return rc;
-  const std::vector<Workspace*>& wss = lease.ws;
+  Workspace* wP = lease[0];
+  Workspace* wX = lease[1];
+  std::vector<Workspace*> wK(lease.ws.begin() + 2, lease.ws.begin() + 2 + 8);
+  std::vector<Workspace*> wss(lease.ws.begin() + 10, lease.ws.end());
+  auto sync_all = [&]() { for (Workspace* w : lease.ws) { cudaStreamSynchronize(w->stream); if (w->ovl) cudaStreamSynchronize(w->ovl); } };
   std::vector<ocmps_mps*> psiH(nchains, nullptr);
   for (int c = 0; c < nchains; ++c) {
-    if (!wss[c]->psiH) {          // kept with the workspace so that its step graphs stay valid across calls
-      rc = alloc_mps(st->ctx, st->L, st->D, st->cap, &wss[c]->psiH);
+    Workspace* ws = wss[c];
+    if (!ws->psiH) {          // kept with the workspace so that its step graphs stay valid across calls
+      rc = alloc_mps(st->ctx, st->L, st->D, st->cap, &ws->psiH);
       if (rc) return rc;
     }
-    psiH[c] = wss[c]->psiH;
-  }
-  // The overlaps <xiH_j|psiH_j> of a row are not taken step by step (60+ dependent small launches per step): the
-  // propagated slices go to a per-chain store of `chunk` slots and are overlapped with the matching xiH slices in one
-  // batched transfer-matrix pass per chunk.
-  int chunk = 32;
-  if (const char* e = getenv("OCMPS_HESSIAN_CHUNK")) chunk = std::max(1, atoi(e));
-  chunk = std::min(chunk, std::max(1, Nt - 2));
-  for (int c = 0; c < nchains; ++c) {
-    Workspace* ws = wss[c];
-    if (ws->rowstore && ws->rowstore->nslots != chunk) {
+    psiH[c] = ws->psiH;
+    if (ws->rowstore && ws->rowstore->nslots != ring) {
       cudaStreamSynchronize(ws->stream);
       cudaFree(ws->rowstore->data); cudaFree(ws->rowstore->dims); cudaFree(ws->rowstore->q); delete ws->rowstore;
       ws->rowstore = nullptr;
     }
     if (!ws->rowstore) {
-      rc = ocmps_store_create(st->ctx, st->L, st->D, st->cap, chunk, &ws->rowstore);
+      rc = ocmps_store_create(st->ctx, st->L, st->D, st->cap, ring, &ws->rowstore);
       if (rc) return rc;
     }
+    if (!ws->ovl) CK(cudaStreamCreateWithFlags(&ws->ovl, cudaStreamNonBlocking));
+    rc = ensure_overlap_bufs(ws, CH, st->cap, st->cap);      // (may reallocate: before anything is in flight)
+    if (rc) return rc;
   }
-  cplx* d_ovl = nullptr;
+  for (int k = 0; k < NK; ++k)
+    if (!wK[k]->tmpK) { rc = alloc_mps(st->ctx, st->L, st->D, st->cap, &wK[k]->tmpK); if (rc) return rc; }
+  const int OB = 64;                                           // slices per batched pass of the divT / fidelity overlaps
+  if (divT) { rc = ensure_overlap_bufs(wX, std::min(OB, Nt), st->cap, st->cap); if (rc) return rc; }
+  if (fid) { rc = ensure_overlap_bufs(wP, std::min(OB, Nt), st->cap, st->cap); if (rc) return rc; }
+
+  cplx *d_ovl = nullptr, *d_div = nullptr, *d_fid = nullptr;
   double* d_norms = nullptr;
+  std::vector<cudaEvent_t> events;
+  auto new_event = [&]() { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); events.push_back(e); return e; };
+  auto cleanup = [&]() {
+    for (cudaEvent_t e : events) if (e) cudaEventDestroy(e);
+    cudaFree(d_ovl); cudaFree(d_norms); cudaFree(d_div); cudaFree(d_fid);
+  };
   CK(cudaMalloc(&d_ovl, sizeof(cplx) * (size_t)Nt * Nt));
   CK(cudaMalloc(&d_norms, sizeof(double) * Nt));
+  CK(cudaMalloc(&d_div, sizeof(cplx) * Nt));
+  CK(cudaMalloc(&d_fid, sizeof(cplx) * Nt));
   CK(cudaMemset(d_ovl, 0, sizeof(cplx) * (size_t)Nt * Nt));
   CK(cudaMemset(d_norms, 0, sizeof(double) * Nt));
   CK(cudaStreamSynchronize(cudaStreamLegacy));
-  // longest rows first, dealt round-robin to the chains.  Host threads (the reference's work-queue threads,
-  // src/OptimalControl.cpp:305-335) each drive a subset of the chains; a thread advances its chains in lock step so
-  // that all of its streams stay fed.
+  std::vector<cudaEvent_t> ev_psi(Nt, nullptr), ev_xi(Nt, nullptr), ev_xiH;
+  if (do_psi) for (int i = 0; i < Nt; ++i) ev_psi[i] = new_event();
+  if (do_xi) for (int i = 0; i < Nt; ++i) ev_xi[i] = new_event();
+  struct ChainEv { std::vector<cudaEvent_t> ready, freed; };
+  std::vector<ChainEv> cev(nchains);
+  for (int c = 0; c < nchains; ++c)
+    for (int m = 0; m < NCH; ++m) { cev[c].ready.push_back(new_event()); cev[c].freed.push_back(new_event()); }
+
   // Work queue (the reference's mutex-guarded row counter, src/OptimalControl.cpp:305-335): rows sorted by decreasing
   // length; a chain that has enqueued the last step of its row takes the next row of the queue.  All chains advance one
-  // step per pass of the loop below, so this is longest-processing-time list scheduling of the rows onto the chains.
+  // step per pass of the loop below, and so do the two sweeps and the K.xi chains, so no stream is ever given work
+  // whose prerequisites have not been enqueued yet.
   std::vector<int> order(rows, rows + nrows);
   std::sort(order.begin(), order.end());
-  struct ChainState { int row = -1; int j = 0; int filled = 0; int j0 = 0; };   // j0: time index of slot 0 of the open chunk
-  std::atomic<int> next_row{0};
+  // A closed chunk waits in `pending` until its overlap pass can be enqueued: the pass has to wait for the events of the
+  // K.xi chains, and a stream can only wait for an event that has already been recorded (enqueued) on the host side.
+  struct Pending { int row, j0, filled, m; };
+  struct ChainState {
+    int row = -1; int j = 0; long long chunk = 0; int filled = 0; int j0 = 0; bool xiH_waited = false;
+    long long flushed = 0;                     // chunks whose overlap pass has been enqueued
+    std::vector<Pending> pending;
+  };
   std::vector<ChainState> cs(nchains);
-  const int hw = (int)std::thread::hardware_concurrency();
-  (void)hw;
-  int nthreads = 1;      // measured: the rows are GPU bound, extra launch threads do not help (OCMPS_HESSIAN_THREADS overrides)
-  if (const char* e = getenv("OCMPS_HESSIAN_THREADS")) nthreads = std::max(1, std::min(nchains, atoi(e)));
-  std::mutex err_mutex;
-  std::string err_msg;
-  int err_rc = OCMPS_OK;
-  auto worker = [&](int t) {
-    cudaSetDevice(st->ctx->dev);
-    int lrc = OCMPS_OK;
-    bool busy = true;
-    while (busy && !lrc) {
-      busy = false;
-      for (int c = t; c < nchains && !lrc; c += nthreads) {
-        ChainState& S = cs[c];
-        Workspace* ws = wss[c];
-        if (S.row < 0) {
-          const int qi = next_row.fetch_add(1);
-          if (qi >= nrows) { next_row.store(nrows); continue; }
-          S.row = order[qi];
-          if (S.row < 1 || S.row > Nt - 2) { lrc = fail(OCMPS_ERR_INVALID, "hessian row out of range [1, Nt-2]"); break; }
-          // psiH = K|psi_row>, its norm, diagonal overlap (src/OptimalControl.cpp:256-264)
-          lrc = store_get_async(psi_store, S.row, ws->work, ws->stream);
-          if (!lrc) lrc = apply_K_async(st, ws, ws->work, psiH[c], ws->stream);
-          if (lrc) break;
-          launch_norm_only(psiH[c]->site(0), psiH[c]->dim(0), psiH[c]->dim(1), st->D, ws->db.partial, d_norms + S.row, 0, ws->stream);
-          g_ocmps_launches += 2;
-          lrc = overlaps_async(ws, side_of_store(xiH_store, S.row), xiH_store->lay, side_of_mps(psiH[c]), psiH[c]->lay, 1, 0, ws->stream);
-          if (lrc) break;
-          if (cudaMemcpyAsync(d_ovl + (size_t)S.row * Nt + S.row, ws->d_out, sizeof(cplx), cudaMemcpyDeviceToDevice, ws->stream) != cudaSuccess) {
-            lrc = fail(OCMPS_ERR_CUDA, "cudaMemcpyAsync failed"); break;
-          }
-          S.j = S.row + 1;
-          S.filled = 0; S.j0 = S.j;
-          busy = true;
-        } else {
-          if (S.j >= Nt - 1) { S.row = -1; busy = true; continue; }
-          // one step forward (:267-277); the slice goes to the chain's chunk store
-          lrc = step_enqueue(st, psiH[c], ws, u[S.j - 1], u[S.j], true, ws->rowstore, S.filled, ws->stream);
-          if (lrc) break;
-          ++S.filled;
-          if (S.filled == chunk || S.j == Nt - 2) {        // chunk full or row finished: overlaps with xiH_{j0 .. j0+filled-1}
-            lrc = overlaps_async(ws, side_of_store(xiH_store, S.j0), xiH_store->lay, side_of_store(ws->rowstore, 0), ws->rowstore->lay,
-                                 S.filled, 0, ws->stream);
-            if (lrc) break;
-            if (cudaMemcpyAsync(d_ovl + (size_t)S.row * Nt + S.j0, ws->d_out, sizeof(cplx) * S.filled, cudaMemcpyDeviceToDevice,
-                                ws->stream) != cudaSuccess) {
-              lrc = fail(OCMPS_ERR_CUDA, "cudaMemcpyAsync failed"); break;
-            }
-            S.filled = 0; S.j0 = S.j + 1;
-          }
-          ++S.j;
-          busy = true;
-        }
+  int next_row = 0;
+  int psi_done = do_psi ? -1 : Nt - 1;      // last psi slice whose store has been enqueued
+  int xi_next = Nt - 1;                      // next xi slice to be produced (counting down); -1: sweep enqueued
+  int kxi_next = Nt - 1;                     // next K.xi slice to enqueue (counting down, the order the xi sweep produces them)
+  bool xiH_recorded = !do_xiH;
+  auto fail_out = [&](int code) { sync_all(); cleanup(); return code; };
+
+  // enqueues the overlap passes of the closed chunks of chain c (K.xi slices j0 .. j0+filled-1 against the chunk) on the
+  // chain's overlap stream -- possible once the events of the K.xi chains exist
+  auto flush_pending = [&](int c) -> int {
+    ChainState& S = cs[c];
+    Workspace* ws = wss[c];
+    if (!xiH_recorded) return OCMPS_OK;
+    for (const Pending& P : S.pending) {
+      cudaStreamWaitEvent(ws->ovl, cev[c].ready[P.m], 0);
+      if (!S.xiH_waited) {
+        for (cudaEvent_t e : ev_xiH) cudaStreamWaitEvent(ws->ovl, e, 0);
+        S.xiH_waited = true;
+      }
+      int lrc = overlaps_async(ws, side_of_store(xiH_store, P.j0), xiH_store->lay, side_of_store(ws->rowstore, P.m * CH), ws->rowstore->lay,
+                               P.filled, 0, ws->ovl);
+      if (lrc) return lrc;
+      if (cudaMemcpyAsync(d_ovl + (size_t)P.row * Nt + P.j0, ws->d_out, sizeof(cplx) * P.filled, cudaMemcpyDeviceToDevice, ws->ovl) != cudaSuccess)
+        return fail(OCMPS_ERR_CUDA, "cudaMemcpyAsync failed");
+      cudaEventRecord(cev[c].freed[P.m], ws->ovl);
+      ++S.flushed;
+    }
+    S.pending.clear();
+    return OCMPS_OK;
+  };
+  // closes the open chunk of chain c
+  auto close_chunk = [&](int c) -> int {
+    ChainState& S = cs[c];
+    Workspace* ws = wss[c];
+    const int m = (int)(S.chunk % NCH);
+    if (cudaEventRecord(cev[c].ready[m], ws->stream) != cudaSuccess) return fail(OCMPS_ERR_CUDA, "cudaEventRecord failed");
+    S.pending.push_back({S.row, S.j0, S.filled, m});
+    ++S.chunk;
+    S.j0 += S.filled;
+    S.filled = 0;
+    return flush_pending(c);
+  };
+  // slot of the ring the next slice of chain c goes to, or -1 if the chain has to pause (on the host side only): the first
+  // slice of a chunk waits until the overlaps that read the chunk's previous contents are done, which requires that pass
+  // to have been enqueued
+  auto next_slot = [&](int c) -> int {
+    ChainState& S = cs[c];
+    const int m = (int)(S.chunk % NCH);
+    if (S.filled == 0 && S.chunk >= NCH) {
+      if (S.flushed < S.chunk - NCH + 1) return -1;
+      cudaStreamWaitEvent(wss[c]->stream, cev[c].freed[m], 0);
+    }
+    return m * CH + S.filled;
+  };
+
+  if (do_psi) {
+    rc = sweep_enqueue_init(st, wP, psi_init, psi_store, 0);
+    if (rc) return fail_out(rc);
+    cudaEventRecord(ev_psi[0], wP->stream);
+    psi_done = 0;
+  }
+  if (do_xi) {
+    rc = sweep_enqueue_init(st, wX, psi_target, xi_store, Nt - 1);
+    if (rc) return fail_out(rc);
+    cudaEventRecord(ev_xi[Nt - 1], wX->stream);
+    // the xi sweep (:393-407) has no prerequisites: all of it goes to its stream right away (a graph launch per step)
+    for (int i = Nt - 1; i > 0; --i) {
+      rc = step_enqueue(st, wX->work, wX, u[i], u[i - 1], false, xi_store, i - 1, wX->stream);
+      if (rc) return fail_out(rc);
+      cudaEventRecord(ev_xi[i - 1], wX->stream);
+    }
+  }
+  xi_next = -1;
+  bool busy = true;
+  while (busy) {
+    busy = false;
+    if (do_psi && psi_done < Nt - 1) {                      // one psi step (:376-390)
+      const int i = psi_done;
+      rc = step_enqueue(st, wP->work, wP, u[i], u[i + 1], true, psi_store, i + 1, wP->stream);
+      if (rc) return fail_out(rc);
+      cudaEventRecord(ev_psi[i + 1], wP->stream);
+      psi_done = i + 1;
+      busy = true;
+    }
+    for (int rep = 0; rep < 2 && do_xiH && kxi_next >= 0 && kxi_next > xi_next; ++rep) {    // K|xi_i> (:300-303), once the slice has been enqueued
+      const int i = kxi_next;
+      Workspace* ws = wK[i % NK];
+      if (ev_xi[i]) cudaStreamWaitEvent(ws->stream, ev_xi[i], 0);
+      rc = store_get_async(xi_store, i, ws->work, ws->stream);
+      if (!rc) rc = apply_K_async(st, ws, ws->work, ws->tmpK, ws->stream);
+      if (!rc) rc = store_put_async(xiH_store, i, ws->tmpK, ws->stream);
+      if (rc) return fail_out(rc);
+      --kxi_next;
+      busy = true;
+      if (kxi_next < 0) {
+        for (int k = 0; k < NK; ++k) { cudaEvent_t e = new_event(); cudaEventRecord(e, wK[k]->stream); ev_xiH.push_back(e); }
+        xiH_recorded = true;
+        for (int c = 0; c < nchains; ++c) { rc = flush_pending(c); if (rc) return fail_out(rc); }
       }
     }
-    if (lrc) {
-      std::lock_guard<std::mutex> lock(err_mutex);
-      if (!err_rc) { err_rc = lrc; err_msg = g_err; }
+    for (int c = 0; c < nchains; ++c) {
+      ChainState& S = cs[c];
+      Workspace* ws = wss[c];
+      if (S.row < 0) {
+        if (next_row >= nrows) continue;
+        if (order[next_row] > psi_done) { busy = true; continue; }     // its psi slice has not been enqueued yet
+        if (S.chunk >= NCH && S.flushed < S.chunk - NCH + 1) { busy = true; continue; }   // ring full until the K.xi events exist
+        S.row = order[next_row++];
+        // psiH = K|psi_row> and its norm (src/OptimalControl.cpp:256-257); the state itself is the first slice of the row
+        if (ev_psi[S.row]) cudaStreamWaitEvent(ws->stream, ev_psi[S.row], 0);
+        rc = store_get_async(psi_store, S.row, ws->work, ws->stream);
+        if (!rc) rc = apply_K_async(st, ws, ws->work, psiH[c], ws->stream);
+        if (rc) return fail_out(rc);
+        launch_norm_only(psiH[c]->site(0), psiH[c]->dim(0), psiH[c]->dim(1), st->D, ws->db.partial, d_norms + S.row, 0, ws->stream);
+        g_ocmps_launches += 2;
+        S.j = S.row; S.j0 = S.row; S.filled = 0;
+        rc = store_put_async(ws->rowstore, next_slot(c), psiH[c], ws->stream);
+        if (rc) return fail_out(rc);
+        ++S.filled;
+        if (S.filled == CH || S.j == Nt - 2) { rc = close_chunk(c); if (rc) return fail_out(rc); }
+        if (S.j == Nt - 2) S.row = -1;
+        ++S.j;
+        busy = true;
+      } else {
+        // one step forward (:267-277); the slice goes to the chain's ring
+        const int slot = next_slot(c);
+        if (slot < 0) { busy = true; continue; }
+        rc = step_enqueue(st, psiH[c], ws, u[S.j - 1], u[S.j], true, ws->rowstore, slot, ws->stream);
+        if (rc) return fail_out(rc);
+        ++S.filled;
+        if (S.filled == CH || S.j == Nt - 2) { rc = close_chunk(c); if (rc) return fail_out(rc); }
+        if (S.j == Nt - 2) S.row = -1;
+        ++S.j;
+        busy = true;
+      }
     }
-  };
-  if (nthreads == 1) {
-    worker(0);
-  } else {
-    std::vector<std::thread> pool;
-    for (int t = 0; t < nthreads; ++t) pool.emplace_back(worker, t);
-    for (auto& th : pool) th.join();
+    if (next_row < nrows) busy = true;
   }
-  rc = err_rc;
-  if (rc) g_err = err_msg;
-  for (Workspace* w : wss) cudaStreamSynchronize(w->stream);
-  if (!rc) {
-    cudaMemcpy(ovl, d_ovl, sizeof(cplx) * (size_t)Nt * Nt, cudaMemcpyDeviceToHost);
-    cudaMemcpy(norms, d_norms, sizeof(double) * Nt, cudaMemcpyDeviceToHost);
+  // tails of the sweep streams: fidelity overlaps <target|psi_i> (:242,450) and divT_i = <xi_i|K|psi_i> (:410-419)
+  if (fid) {
+    for (int z0 = 0; z0 < Nt; z0 += OB) {
+      const int nb = std::min(OB, Nt - z0);
+      rc = overlaps_async(wP, side_of_mps(psi_target), psi_target->lay, side_of_store(psi_store, z0), psi_store->lay, nb, 0, wP->stream);
+      if (rc) return fail_out(rc);
+      cudaMemcpyAsync(d_fid + z0, wP->d_out, sizeof(cplx) * nb, cudaMemcpyDeviceToDevice, wP->stream);
+    }
   }
-  cudaFree(d_ovl); cudaFree(d_norms);
-  if (rc) return rc;
+  if (divT) {
+    if (do_psi) cudaStreamWaitEvent(wX->stream, ev_psi[Nt - 1], 0);
+    for (int z0 = 0; z0 < Nt; z0 += OB) {
+      const int nb = std::min(OB, Nt - z0);
+      rc = overlaps_async(wX, side_of_store(xi_store, z0), xi_store->lay, side_of_store(psi_store, z0), psi_store->lay, nb, 1, wX->stream);
+      if (rc) return fail_out(rc);
+      cudaMemcpyAsync(d_div + z0, wX->d_out, sizeof(cplx) * nb, cudaMemcpyDeviceToDevice, wX->stream);
+    }
+  }
+  sync_all();
+  cudaMemcpy(ovl, d_ovl, sizeof(cplx) * (size_t)Nt * Nt, cudaMemcpyDeviceToHost);
+  cudaMemcpy(norms, d_norms, sizeof(double) * Nt, cudaMemcpyDeviceToHost);
+  if (divT) cudaMemcpy(divT, d_div, sizeof(cplx) * Nt, cudaMemcpyDeviceToHost);
+  if (fid) cudaMemcpy(fid, d_fid, sizeof(cplx) * Nt, cudaMemcpyDeviceToHost);
+  cleanup();
   return lease.finish();
+}
+
+int ocmps_hessian_rows(ocmps_stepper* st, ocmps_store* psi_store, ocmps_store* xiH_store, const double* u, int Nt, const int* rows,
+                       int nrows, int nchains, double* ovl, double* norms) {
+  return hessian_run(st, nullptr, nullptr, u, Nt, psi_store, nullptr, xiH_store, rows, nrows, nchains, 0, 0, 0, nullptr, nullptr, ovl, norms);
+}
+
+int ocmps_hessian_eval(ocmps_stepper* st, ocmps_mps* psi_init, ocmps_mps* psi_target, const double* u, int Nt, ocmps_store* psi_store,
+                       ocmps_store* xi_store, ocmps_store* xiH_store, const int* rows, int nrows, int nchains, int do_psi, int do_xi,
+                       double* divT, double* fid, double* ovl, double* norms) {
+  if (!psi_target || !divT || !fid) return fail(OCMPS_ERR_INVALID, "null argument");
+  return hessian_run(st, psi_init, psi_target, u, Nt, psi_store, xi_store, xiH_store, rows, nrows, nchains, do_psi ? 1 : 0, do_xi ? 1 : 0, 1,
+                     divT, fid, ovl, norms);
 }
 
 }  // extern "C"

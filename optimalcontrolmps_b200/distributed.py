@@ -69,17 +69,25 @@ def allgather_array(local: np.ndarray, device=None) -> List[np.ndarray]:
     return [o.cpu().numpy() for o in outs]
 
 
-def sharded_hessian(oc, control, new_control: bool = True, device=None) -> np.ndarray:
-    """GRAPE Hessian in the control u with rows sharded over the ranks of the default process group.
-    ``oc`` is an optimalcontrolmps_b200.OptimalControl living on this rank's GPU."""
+def sharded_hessian(oc, control, new_control: bool = True, device=None, convert: bool = False) -> np.ndarray:
+    """Hessian with rows sharded over the ranks of the default process group (``calcHessian_parallel`` with the row
+    work queue of src/OptimalControl.cpp:305-335 dealt to GPUs instead of threads).  ``oc`` is an
+    optimalcontrolmps_b200.OptimalControl living on this rank's GPU.  Every rank runs the prerequisites (both sweeps,
+    K.xi) itself -- its rows trail its own psi sweep, so they are not on the critical path -- and its share of the
+    rows; the row blocks are combined with ONE all-gather.  Returns the GRAPE Hessian in u (N x N), or with
+    ``convert=True`` what ``getHessian`` returns (GROUP: V^T H V, src/ControlBasis.cpp:95-119)."""
     import torch.distributed as dist
     world, rank = dist.get_world_size(), dist.get_rank()
     N = oc.getN()
     oc.rows = partition_rows(N, world, rank)
-    u = control if oc.GRAPE else oc.basis.convertControl(control, new_control)
-    oc._calcHessian(u, new_control)
-    max_rows = max(len(partition_rows(N, world, r)) for r in range(world))
-    blocks = allgather_array(pack_rows(oc._hessian_fidelity_part, oc.rows, max_rows), device)
+    try:
+        u = control if oc.GRAPE else oc.basis.convertControl(control, new_control)
+        oc._calcHessian(u, new_control)
+        max_rows = max(len(partition_rows(N, world, r)) for r in range(world))
+        blocks = allgather_array(pack_rows(oc._hessian_fidelity_part, oc.rows, max_rows), device)
+    finally:
+        oc.rows = None
     H = oc._hessian_reg_part + unpack_rows(blocks, N)
-    oc.rows = None
+    if convert and not oc.GRAPE:
+        return np.array(oc.basis.convertHessian(H))
     return H
