@@ -692,13 +692,13 @@ class OptimalControl:
         ovl = ovl.view(np.complex128).reshape(N, N)
         ts2 = self.tstep * self.tstep
         Hf = np.zeros((N, N))
+        dT = self.divT
         for r in rows:
             r = int(r)
-            Hf[r, r] += ts2 * ((of * ovl[r, r]).real - (self.divT[r] * np.conj(self.divT[r])).real)        # :260-264
-            for j in range(r + 1, N - 1):
-                v = ts2 * ((of * ovl[r, j] * norms[r]).real - (self.divT[r] * np.conj(self.divT[j])).real)  # :272-277
-                Hf[r, j] += v
-                Hf[j, r] += v
+            Hf[r, r] += ts2 * ((of * ovl[r, r]).real - (dT[r] * np.conj(dT[r])).real)                      # :260-264
+            v = ts2 * ((of * ovl[r, r + 1:N - 1] * norms[r]).real - (dT[r] * np.conj(dT[r + 1:N - 1])).real)   # :272-277
+            Hf[r, r + 1:N - 1] += v
+            Hf[r + 1:N - 1, r] += v
         self._hessian_fidelity_part = Hf
         self._hessian_reg_part = H
         return H + Hf

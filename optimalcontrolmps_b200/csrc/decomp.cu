@@ -21,6 +21,7 @@
 // One CTA per block in 1 and 2.  Both are bound by instruction issue and dependent latency on that one SM (see
 // profiles/r01_kernel_shares.md), so the code is specialised at compile time on the block shape wherever it is hot.
 #include <cstdio>
+#include <cstdlib>
 #include "ocmps_internal.h"
 
 // development counters: [0] sum of sweeps, [1] blocks, [2] max sweeps, [3] sweeps of blocks with nv >= 64, [4] such blocks,
@@ -1448,7 +1449,7 @@ void profile_read(double* out) {
 }
 
 void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_launch, size_t smem_limit, bool need_global,
-                          bool long_rows, double rank_tol, cudaStream_t s) {
+                          bool long_rows, double rank_tol, int max_rows, cudaStream_t s) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof_on) {
     if (g_prof_used == g_prof_events.size()) {
@@ -1478,6 +1479,7 @@ void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_
   if (long_rows) jacobi_blocks_kernel<true, false><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
   if (need_global) jacobi_blocks_kernel<false, false><<<nblk_launch, JAC_THREADS, 0, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
   // (after ALL first-stage variants: each of them publishes the hand-over flag of the blocks it owns)
+  (void)max_rows;
   jacobi_rot_kernel<<<nblk_launch, JAC_THREADS, JAC_BLOCKED_ROWS * 16 * JAC_EPL * sizeof(cplx), s>>>(a, b);
 }
 

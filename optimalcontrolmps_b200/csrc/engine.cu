@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <string>
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -221,11 +222,17 @@ void free_mps(ocmps_mps* m) {
   delete m;
 }
 
-int alloc_ws(ocmps_ctx* ctx, int L, int D, int cap, bool with_work, Workspace** out) {
+int alloc_ws(ocmps_ctx* ctx, int L, int D, int cap, bool with_work, Workspace** out, bool high_priority = false) {
   Workspace* w = new Workspace();
   w->ctx = ctx; w->L = L; w->D = D; w->cap = cap;
   CK(cudaSetDevice(ctx->dev));
-  CK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+  // The first two workspaces of a shape serve the psi / xi sweeps (leases hand out the lowest-numbered free workspaces):
+  // their streams get the highest priority, so that the sweeps -- the critical path of a Hessian whose rows trail the psi
+  // sweep -- are not queued behind the CTAs of dozens of row chains.  Kernel nodes of captured graphs inherit it.
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  const int prio = high_priority ? prio_hi : prio_lo;
+  CK(cudaStreamCreateWithPriority(&w->stream, cudaStreamNonBlocking, prio));
   const size_t nD = (size_t)cap * D;
   CK(cudaMalloc(&w->theta, sizeof(cplx) * nD * nD));
   CK(cudaMalloc(&w->cbuf, sizeof(cplx) * (size_t)cap * cap));
@@ -257,7 +264,7 @@ int alloc_ws(ocmps_ctx* ctx, int L, int D, int cap, bool with_work, Workspace** 
   CK(cudaMalloc(&w->db2.ywork, sizeof(cplx) * 2 * ywhalf));
   CK(cudaMalloc(&w->db2.scratch_d, sizeof(double) * 8 * NV_MAX));
   CK(cudaMalloc(&w->db2.descs, sizeof(GemmDesc) * 4));
-  CK(cudaStreamCreateWithFlags(&w->side, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithPriority(&w->side, cudaStreamNonBlocking, prio));
   CK(cudaEventCreateWithFlags(&w->ev_trunc, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&w->ev_setup, cudaEventDisableTiming));
   if (with_work) {
@@ -336,7 +343,9 @@ struct WsLease {
     }
     while ((int)ws.size() < n) {
       Workspace* w = nullptr;
-      int rc = alloc_ws(c, L, D, cap, true, &w);
+      int same = 0;
+      for (Workspace* o : c->pool) if (o->L == L && o->D == D && o->cap == cap) ++same;
+      int rc = alloc_ws(c, L, D, cap, true, &w, same < 2);
       if (rc) return rc;
       w->busy = true;
       c->pool.push_back(w);
@@ -483,6 +492,27 @@ std::vector<Op> build_schedule(int L) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// development trace (OCMPS_STEP_TRACE=1, plain launches): CUDA events between the phases of every decomposition
+// ------------------------------------------------------------------------------------------------
+struct StepTrace {
+  bool on = false;
+  std::vector<std::pair<int, cudaEvent_t>> marks;     // (phase that ENDS at this mark, event)
+  void mark(int phase, cudaStream_t s) {
+    if (!on) return;
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    marks.push_back({phase, e});
+  }
+};
+static StepTrace g_trace;
+static bool step_trace_enabled() {
+  static const bool v = [] { const char* e = getenv("OCMPS_STEP_TRACE"); return e && e[0] == '1'; }();
+  return v;
+}
+enum { TR_START = 0, TR_MERGE, TR_SETUP, TR_SVD_GATE, TR_SVD_ORTH, TR_TRUNC, TR_BUILD, TR_OTHER, TR_NPHASE };
+
+// ------------------------------------------------------------------------------------------------
 // decomposition driver
 // ------------------------------------------------------------------------------------------------
 // setup -> QR + Jacobi per charge block -> global truncation -> assembly of isometry and centre factor
@@ -492,7 +522,7 @@ std::vector<Op> build_schedule(int L) {
 void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int capV, int capC, int capK, cudaStream_t s,
                 DecompBuffers* dbp = nullptr, bool setup_done = false, const DecompArgs* next = nullptr, DecompBuffers* db_next = nullptr) {
   DecompBuffers& db = dbp ? *dbp : ws->db;
-  if (!setup_done) launch_decomp_setup(a, db, s);
+  if (!setup_done) { launch_decomp_setup(a, db, s); g_trace.mark(TR_SETUP, s); }
   // shared memory: the largest block has at most capV vectors of at most capC components
   size_t need = (size_t)capV * capC * sizeof(cplx);
   // the Jacobi working set stores its rows (<= min(capV, capC) of them) with a stride padded to a multiple of 16
@@ -508,8 +538,11 @@ void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int c
   double rank_tol = rank_scale * tp.cutoff;
   rank_tol = std::min(rank_scale * 1e-8, std::max(1e-30, rank_tol));
   const bool long_rows = capV > 128;                   // rows of R longer than the register-cached path handles
-  launch_jacobi_blocks(a, db, nblk, smem, need_global, long_rows, rank_tol, s);
+  const int max_rows = std::min(capV, capC);           // rows of R of the largest possible block
+  launch_jacobi_blocks(a, db, nblk, smem, need_global, long_rows, rank_tol, max_rows, s);
+  g_trace.mark((a.kind == DK_GATE_LEFT || a.kind == DK_GATE_RIGHT) ? TR_SVD_GATE : TR_SVD_ORTH, s);
   launch_truncate(a, db, tp, s);
+  g_trace.mark(TR_TRUNC, s);
   if (next) {
     cudaEventRecord(ws->ev_trunc, s);
     cudaStreamWaitEvent(ws->side, ws->ev_trunc, 0);
@@ -517,6 +550,7 @@ void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int c
     cudaEventRecord(ws->ev_setup, ws->side);
   }
   launch_build_factors(a, db, capK, capV, capC, s);
+  g_trace.mark(TR_BUILD, s);
   g_ocmps_launches += 5 + (need_global ? 1 : 0) + (long_rows ? 1 : 0);
 }
 
@@ -594,6 +628,7 @@ void run_step_body(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, cudaStream_t 
       if (fused_merge && D >= 2 && D <= 8) {
         launch_merge_gate(m->site(j1), m->site(j2), ws->theta, m->dim(bl), m->dim(bm), m->dim(br), m->q(bl), m->q(bm), m->q(br), D, sp,
                           op.b, lay.capb[bl], lay.capb[br], s);
+        g_trace.mark(TR_MERGE, s);
         g_ocmps_launches -= 2;
       } else {
         launch_merge_setup(ws->db.descs + 2, m->site(j1), m->site(j2), ws->theta, m->dim(bl), m->dim(bm), m->dim(br), D, s);
@@ -697,6 +732,33 @@ int step_enqueue(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, double from, do
       g_ocmps_launches += 1;
     }
   };
+  if (step_trace_enabled()) {          // plain launches with an event after every phase; prints the phase sums of this step
+    CK(cudaStreamSynchronize(s));
+    g_trace.on = true;
+    g_trace.marks.clear();
+    g_trace.mark(TR_START, s);
+    body();
+    g_trace.mark(TR_OTHER, s);
+    g_trace.on = false;
+    CK(cudaStreamSynchronize(s));
+    double sum[TR_NPHASE] = {0};
+    int cnt[TR_NPHASE] = {0};
+    for (size_t i = 1; i < g_trace.marks.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, g_trace.marks[i - 1].second, g_trace.marks[i].second);
+      sum[g_trace.marks[i].first] += ms;
+      ++cnt[g_trace.marks[i].first];
+    }
+    float tot = 0.f;
+    cudaEventElapsedTime(&tot, g_trace.marks.front().second, g_trace.marks.back().second);
+    static const char* names[TR_NPHASE] = {"", "merge_gate", "setup", "svd(gate)", "svd(gauge)", "truncate", "build", "other"};
+    fprintf(stderr, "[ocmps step] %.3f ms:", tot);
+    for (int p = 1; p < TR_NPHASE; ++p) fprintf(stderr, " %s %dx %.3f |", names[p], cnt[p], sum[p]);
+    fprintf(stderr, "\n");
+    for (auto& m2 : g_trace.marks) cudaEventDestroy(m2.second);
+    g_trace.marks.clear();
+    return OCMPS_OK;
+  }
   if (!graphs_enabled() || profile_is_on()) { body(); return OCMPS_OK; }   // event timing needs plain launches
   unsigned long long parity = 0;
   for (int j = 0; j < lay.L; ++j) parity |= (unsigned long long)(m->cur[j] & 1) << j;
@@ -1729,6 +1791,12 @@ static int hessian_run(ocmps_stepper* st, ocmps_mps* psi_init, ocmps_mps* psi_ta
   int kxi_next = Nt - 1;                     // next K.xi slice to enqueue (counting down, the order the xi sweep produces them)
   bool xiH_recorded = !do_xiH;
   auto fail_out = [&](int code) { sync_all(); cleanup(); return code; };
+  // development trace (OCMPS_HESSIAN_TRACE=1): when the sweeps, the K.xi store and everything finished, on the device clock
+  static const bool trace = [] { const char* e = getenv("OCMPS_HESSIAN_TRACE"); return e && e[0] == '1'; }();
+  cudaEvent_t tr[4] = {nullptr, nullptr, nullptr, nullptr};
+  const auto host_t0 = std::chrono::steady_clock::now();
+  double host_enq_ms = 0.0;
+  if (trace) { for (auto& e : tr) cudaEventCreate(&e); cudaEventRecord(tr[0], wP->stream); }
 
   // enqueues the overlap passes of the closed chunks of chain c (K.xi slices j0 .. j0+filled-1 against the chunk) on the
   // chain's overlap stream -- possible once the events of the K.xi chains exist
@@ -1861,6 +1929,12 @@ static int hessian_run(ocmps_stepper* st, ocmps_mps* psi_init, ocmps_mps* psi_ta
     }
     if (next_row < nrows) busy = true;
   }
+  if (trace) {
+    cudaEventRecord(tr[1], wP->stream);
+    cudaEventRecord(tr[2], wX->stream);
+    if (NK > 0) cudaEventRecord(tr[3], wK[0]->stream);
+    host_enq_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+  }
   // tails of the sweep streams: fidelity overlaps <target|psi_i> (:242,450) and divT_i = <xi_i|K|psi_i> (:410-419)
   if (fid) {
     for (int z0 = 0; z0 < Nt; z0 += OB) {
@@ -1880,6 +1954,16 @@ static int hessian_run(ocmps_stepper* st, ocmps_mps* psi_init, ocmps_mps* psi_ta
     }
   }
   sync_all();
+  if (trace) {
+    const double host_all_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+    float a = 0.f, bq = 0.f, c = 0.f;
+    cudaEventElapsedTime(&a, tr[0], tr[1]);
+    cudaEventElapsedTime(&bq, tr[0], tr[2]);
+    if (NK > 0) cudaEventElapsedTime(&c, tr[0], tr[3]);
+    fprintf(stderr, "[ocmps hessian] rows %d chains %d ring %dx%d | host: enqueue %.1f ms, all done %.1f ms | device: psi sweep %.1f ms, xi sweep %.1f ms, "
+                    "K.xi chain 0 %.1f ms\n", nrows, nchains, NCH, CH, host_enq_ms, host_all_ms, a, bq, c);
+    for (auto& e : tr) cudaEventDestroy(e);
+  }
   cudaMemcpy(ovl, d_ovl, sizeof(cplx) * (size_t)Nt * Nt, cudaMemcpyDeviceToHost);
   cudaMemcpy(norms, d_norms, sizeof(double) * Nt, cudaMemcpyDeviceToHost);
   if (divT) cudaMemcpy(divT, d_div, sizeof(cplx) * Nt, cudaMemcpyDeviceToHost);

@@ -117,7 +117,7 @@ struct DecompBuffers {
 
 void launch_decomp_setup(const DecompArgs& a, const DecompBuffers& b, cudaStream_t s);
 void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_launch, size_t smem_limit, bool need_global,
-                          bool long_rows, double rank_tol, cudaStream_t s);
+                          bool long_rows, double rank_tol, int max_rows, cudaStream_t s);
 void launch_spectrum_entropy(const DecompBuffers& b, double* out, cudaStream_t s);
 void launch_truncate(const DecompArgs& a, const DecompBuffers& b, const TruncParams& tp, cudaStream_t s);
 void launch_build_factors(const DecompArgs& a, const DecompBuffers& b, int cap_k, int cap_vec, int cap_comp, cudaStream_t s);

@@ -1,3 +1,2 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-python bench.py --steps 1 --warmup 1 --no-cpu-baseline --batch 0 > gpurun_out/r02_bench_hess1.json 2> gpurun_out/r02_bench_hess1.err
-tail -c 1500 gpurun_out/r02_bench_hess1.json; tail -5 gpurun_out/r02_bench_hess1.err
+OCMPS_STEP_TRACE=1 python tools/gpu_prof_at.py 175 3 2>&1 | grep -v "^block" | tail -5
+OCMPS_STEP_TRACE=1 python tools/gpu_prof_at.py 30 2 2>&1 | grep "ocmps step" | tail -2

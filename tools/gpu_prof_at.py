@@ -18,6 +18,9 @@ pd = st.to_device(ground_state(L, d, CFG["Npart"], CFG["U_i"]))
 for k in range(K):
     st.step(pd, u[k], u[k + 1], True)
 rt = ctypes.CDLL("/usr/local/cuda/lib64/libcudart.so")
+lib = st.ctx.lib
+_d = (ctypes.c_ulonglong * 8)()
+lib.ocmps_debug_jacobi(_d, 1)
 rt.cudaProfilerStart()
 t0 = time.perf_counter()
 for k in range(K, K + P):
@@ -25,3 +28,8 @@ for k in range(K, K + P):
 t1 = time.perf_counter()
 rt.cudaProfilerStop()
 print("steps", K, "..", K + P, "ms per step", (t1 - t0) / P * 1e3, "dims", pd.bond_dims())
+dbg = (ctypes.c_ulonglong * 8)()
+lib.ocmps_debug_jacobi(dbg, 0)
+nb = max(dbg[4], 1)
+print("block SVDs", dbg[1], "sweeps", dbg[0], "max sweeps", dbg[2], "| blocks with >= 64 vectors:", dbg[4], "sweeps/blk", dbg[3] / nb,
+      "QR kclk/blk", dbg[5] / nb / 1e3, "Jacobi kclk/blk", dbg[6] / nb / 1e3, "total kclk/blk", dbg[7] / nb / 1e3)

@@ -13,7 +13,7 @@ L, d = CFG["L"], CFG["d"]
 st = oc.BH_tDMRG(oc.BoseHubbard(L, d), CFG["J"], CFG["tstep"], oc.Args("Cutoff=", CFG["cutoff"], "Maxm=", CFG["maxm"]))
 basis, c, u = bench.make_problem_host(0)
 N = len(u)
-for name, start, fwd in (("psi", ground_state(L, d, CFG["Npart"], CFG["U_i"]), True), ("xi", ground_state(L, d, CFG["Npart"], CFG["U_f"]), False)):
+for name, start, fwd in (("psi", ground_state(L, d, CFG["Npart"], CFG["U_i"]), True),):
     for rep in range(2):          # second pass: step graphs are captured
         pd = st.to_device(start)
         ts = []
