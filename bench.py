@@ -39,6 +39,15 @@ def nt():
     return int(CFG["T"] / CFG["tstep"] + 1)
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    """Progress on stderr (the JSON line on stdout is printed once, at the end)."""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def config_dict():
     """The `config` object of the JSON line -- identical in both arms."""
     return {"workload": "cfg2: BH L=20 Npart=20 d=5 T=2.0 tstep=0.01 GROUP M=10 chi=100, one cost+gradient evaluation "
@@ -226,7 +235,7 @@ def run_reference(args):
     hess_est = None
     if "fwd_step_s" in det:
         hess_est = (N - 2) * (N - 1) / 2.0 * det["fwd_step_s"] + 2 * (N - 1) * det["fwd_step_s"]
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "n_gpus_requested": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_eval * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "complex128 (f64)", "data": "synthetic",
             "config": config_dict(),
@@ -298,8 +307,10 @@ def run_ours(args):
         cost = ocp.getCost(list(c), False)
         return cost, g
 
+    log("cfg2: warm-up evaluations")
     for _ in range(args.warmup):
         one_eval()
+    log("cfg2: timed evaluations")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -351,6 +362,7 @@ def run_ours(args):
 
     if rank == 0:
         # ---- roofline of the dominant kernel (block SVD), event-timed on its own streams in one extra eval ----
+        log("cfg2: roofline evaluation (block-SVD kernels event-timed)")
         lib.ocmps_profile_enable(1)
         one_eval()
         out4 = np.zeros(4)
@@ -379,6 +391,7 @@ def run_ours(args):
                             "peak_source": "measured in this run: cuBLAS DGEMM 4096^3 burst (MEASURED_PEAKS.json has no FP64 figure)"}
         if world == 1 and not args.no_cpu_baseline:
             # ---- CPU baseline: the oracle port on this box's host cores, bounded sample taken at real slices ----
+            log("cfg2: CPU baseline sample")
             from oracle import bh_mps as ob
             conv = lambda h: ob.MPS(h.A, [np.asarray(x, dtype=np.int64) for x in h.q], 0, 2)
             idx = [int(round(x)) for x in np.linspace(4, N - 5, 8)]
@@ -391,12 +404,36 @@ def run_ours(args):
                                               f"overlap from each of 8 evenly spaced slices of this run's psi_t / xi_t, extrapolated to "
                                               f"2*(Nt-1) steps + Nt+1 overlaps", **det}
         if args.batch > 1 and world == 1:
+            log(f"cfg2: {args.batch} controls in flight")
             line["batched"] = batched_bench(args.batch, oc, st, psi_i, psi_f, ocp, c)
-        if args.hessian_nt:
-            line["hessian"] = hessian_bench(args.hessian_nt, oc, ocd, st, psi_i, psi_f, world, rank, dev, torch)
+        with_cpu = world == 1 and not args.no_cpu_baseline
+        if args.cfg1 and world == 1:
+            log("cfg1 block")
+            line["cfg1"] = cfg1_bench(oc, ctx, peak, with_cpu)
+        if args.cfg5 and world == 1:
+            log("cfg5 block")
+            ctx.trim()
+            line["cfg5"] = cfg5_bench(oc, ctx, peak, with_cpu)
+    # blocks every rank takes part in
+    ctx.trim()
+    del ocp                                           # (frees 5.7 GB of slice stores before the larger workloads)
+    if args.hessian_nt:
+        log("cfg3 Hessian block")
+        hb = hessian_bench(args.hessian_nt, oc, ocd, st, psi_i, psi_f, world, rank, dev, torch)
+        if rank == 0:
+            line["hessian"] = hb
+    if args.cfg4_seeds > 0:
+        log("cfg4 block")
+        ctx.trim()                                    # the Hessian's 58 chains own ~100 GB of rings at the cfg2 shape
+        c4, probs4, ctrls4, st4 = cfg4_bench(oc, ocd, ctx, world, rank, dev, torch, args.cfg4_seeds, args.cfg4_inflight)
+        if rank == 0:
+            if world == 1 and not args.no_cpu_baseline:
+                c4["cpu_baseline"] = cfg4_cpu_sample(probs4, st4)
+            line["cfg4"] = c4
+        del probs4
+    log("done")
+    if rank == 0:
         print(json.dumps(line), flush=True)
-    elif args.hessian_nt:
-        hessian_bench(args.hessian_nt, oc, ocd, st, psi_i, psi_f, world, rank, dev, torch)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -419,6 +456,220 @@ def batched_bench(B, oc, st, psi_i, psi_f, ocp0, c0):
     c1 = probs[0].getCost(ctrls[0], False)
     return {"evals_in_flight": B, "value": B / dt, "unit": UNIT, "seconds": dt,
             "max_abs_diff_vs_single": float(max(abs(res[0][0] - c1), np.max(np.abs(np.array(res[0][1]) - np.array(g1)))))}
+
+
+# ----------------------------------------------------------------------------------------------
+# the other configs of BASELINE.json as sub-blocks of the line (each with its own CPU sample)
+# ----------------------------------------------------------------------------------------------
+CFG1 = dict(L=5, d=4, Npart=5, J=1.0, T=2.0, tstep=0.01, maxm=80, cutoff=1e-8, gamma=1e-6, U_i=2.5, U_f=50.0)
+CFG4 = dict(L=30, d=5, Npart=30, J=1.0, T=2.0, tstep=0.01, M=10, maxm=150, cutoff=1e-8, gamma=1e-6, U_i=2.5, U_f=50.0)
+CFG5 = dict(L=50, d=5, Npart=50, J=1.0, T=5.0, tstep=0.01, maxm=256, cutoff=1e-10, gamma=1e-6)
+
+
+def cfg1_control():
+    import optimalcontrolmps_b200 as oc
+    N = int(CFG1["T"] / CFG1["tstep"] + 1)
+    u0 = np.array(oc.SeedGenerator.linsigmoidSeed(CFG1["U_i"], CFG1["U_f"], N, np.random.default_rng(7)))
+    return np.clip(u0 + np.random.default_rng(2024).uniform(-0.5, 0.5, N), 2.0, 100.0)
+
+
+def svd_roofline(lib, fn, peak):
+    """Runs fn() once with the block-SVD kernels event-timed on their own streams; returns the roofline object."""
+    import ctypes
+    lib.ocmps_profile_enable(1)
+    fn()
+    out4 = np.zeros(4)
+    lib.ocmps_profile_read(out4.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    lib.ocmps_profile_enable(0)
+    ms_tot, nl, fl_blk, fl_dense = out4
+    ach = fl_blk / (ms_tot * 1e-3) / 1e12 if ms_tot > 0 else 0.0
+    return {"kernel": "jacobi_blocks_kernel + jacobi_rot_kernel", "bound": "latency", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+            "frac": ach / peak if peak else None, "traffic": None, "launches": int(nl), "avg_launch_us": ms_tot * 1e3 / max(nl, 1),
+            "algorithmic_flops": "block-summed F_gram+F_evd (SURVEY.md 8d)"}
+
+
+def cfg1_bench(oc, ctx, peak, with_cpu):
+    """BASELINE.json configs[0], the README input (README.md:30-45): L=5 Npart=5 d=4, T=2, Nt=201, Maxm=80, GRAPE.  The GPU runs
+    the complete evaluation through the public API; the CPU port runs the complete evaluation too (it takes seconds)."""
+    from optimalcontrolmps_b200.states import ground_state
+    c = CFG1
+    st = oc.BH_tDMRG(oc.BoseHubbard(c["L"], c["d"]), c["J"], c["tstep"], oc.Args("Cutoff=", c["cutoff"], "Maxm=", c["maxm"]), ctx=ctx)
+    psi_i = ground_state(c["L"], c["d"], c["Npart"], c["U_i"])
+    psi_f = ground_state(c["L"], c["d"], c["Npart"], c["U_f"])
+    u = list(cfg1_control())
+    N = len(u)
+    p = oc.OptimalControl(psi_f, psi_i, st, N, c["gamma"])
+    p.setThreadCount(2)
+
+    def one():
+        g = p.getAnalyticGradient(u, True)
+        return p.getCost(u, False), g
+
+    for _ in range(3):
+        one()
+    K = 5
+    t0 = time.perf_counter()
+    for _ in range(K):
+        cost, g = one()
+    dt = (time.perf_counter() - t0) / K
+    out = {"workload": "cfg1 (README input): BH L=5 Npart=5 d=4 T=2.0 tstep=0.01 Maxm=80 GRAPE, one cost+gradient evaluation", "value": 1.0 / dt,
+           "unit": UNIT, "ms_per_eval": dt * 1e3, "steps": K, "cost": float(cost), "grad_norm": float(np.linalg.norm(g)),
+           "max_bond_dim": int(p.psi_t.bond_dims().max()), "roofline": svd_roofline(ctx.lib, one, peak)}
+    if with_cpu:
+        from oracle import bh_mps as ob, optimal_control as oo
+        conv = lambda h: ob.MPS(h.A, [np.asarray(x, dtype=np.int64) for x in h.q], 0, 2)
+        so = ob.BHStepper(c["L"], c["d"] + 1, c["J"], c["tstep"], ob.TruncArgs(cutoff=c["cutoff"], maxm=c["maxm"]))
+        po = oo.OptimalControl(conv(psi_f), conv(psi_i), so, N=N, gamma=c["gamma"])
+        t0 = time.perf_counter()
+        go = po.getAnalyticGradient(u, True)
+        co = po.getCost(u, False)
+        dtc = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 1.0 / dtc, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                               "sample": "oracle port, one COMPLETE cfg1 evaluation", "seconds": dtc,
+                               "cost_rel_diff_vs_gpu": abs(co - cost) / abs(co),
+                               "grad_rel_diff_vs_gpu": float(np.max(np.abs(np.array(go) - np.array(g))) / np.max(np.abs(go)))}
+    return out
+
+
+def cfg4_bench(oc, ocd, ctx, world, rank, dev, torch, seeds_per_gpu, inflight):
+    """BASELINE.json configs[3]: batched random-seed controls (SeedGenerator fan-out), BH L=30 Npart=30 d=5 chi=150; every GPU
+    evaluates `seeds_per_gpu` controls (seeds 1 + rank*spg ...; 64 seeds = 8 per GPU on 8 GPUs), `inflight` of them at a time
+    (a control owns two slice stores of 10.6 GB at this shape), results combined with one all-gather.  Weak scaling over GPUs."""
+    import torch.distributed as dist
+    from optimalcontrolmps_b200.states import ground_state
+    c = CFG4
+    st = oc.BH_tDMRG(oc.BoseHubbard(c["L"], c["d"]), c["J"], c["tstep"], oc.Args("Cutoff=", c["cutoff"], "Maxm=", c["maxm"]), ctx=ctx)
+    psi_i = ground_state(c["L"], c["d"], c["Npart"], c["U_i"])
+    psi_f = ground_state(c["L"], c["d"], c["Npart"], c["U_f"])
+    N = int(c["T"] / c["tstep"] + 1)
+    u0 = oc.SeedGenerator.linsigmoidSeed(c["U_i"], c["U_f"], N, np.random.default_rng(7))
+    ref_basis = oc.ControlBasisFactory.buildChoppedSineBasis(u0, c["tstep"], c["T"], c["M"])
+    ctrls = []
+    for k in range(seeds_per_gpu):
+        seed = 1 + rank * seeds_per_gpu + k
+        cc = np.array(oc.SeedGenerator.randomCoeffSeed(-4.0, 4.0, c["M"], np.random.default_rng(4000 + seed)))
+        for _ in range(40):
+            uu = np.array(ref_basis.convertControl(list(cc)))
+            if uu.min() >= 2.0 and uu.max() <= 100.0:
+                break
+            cc *= 0.8
+        ctrls.append(list(cc))
+    inflight = max(1, min(inflight, seeds_per_gpu))
+
+    def make(n):       # (a basis caches its last control, so every problem gets its own)
+        return [oc.OptimalControl(psi_f, psi_i, st, oc.ControlBasisFactory.buildChoppedSineBasis(u0, c["tstep"], c["T"], c["M"]), c["gamma"])
+                for _ in range(n)]
+
+    probs = make(inflight)
+    oc.batch_cost_gradient(probs, ctrls[:inflight])         # warm-up (allocates the per-chain workspaces, captures graphs)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    res = []
+    for k0 in range(0, seeds_per_gpu, inflight):
+        cs = ctrls[k0:k0 + inflight]
+        res += oc.batch_cost_gradient(probs[:len(cs)], cs)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    mine = np.concatenate([np.concatenate([[r[0]], r[1]]) for r in res])
+    if world > 1:
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt[0])
+        allres = ocd.allgather_array(mine, dev)
+    else:
+        allres = [mine]
+    out = {"workload": f"cfg4: {seeds_per_gpu * world} random-seed controls ({seeds_per_gpu} per GPU, {inflight} in flight), BH L=30 Npart=30 d=5 "
+                       f"chi=150 GROUP M=10 T=2.0, cost+gradient each", "n_gpus": world, "scaling": "weak", "seeds": seeds_per_gpu * world,
+           "value": seeds_per_gpu * world / dt, "unit": UNIT, "seconds": dt, "max_bond_dim": int(max(p.psi_t.bond_dims().max() for p in probs)),
+           "mean_cost": float(np.mean([a.reshape(seeds_per_gpu, -1)[:, 0] for a in allres]))}
+    return out, probs, ctrls, st
+
+
+def cfg4_cpu_sample(probs, st_cfg):
+    """CPU port on one forward + one backward step + one MPO overlap at 4 slices of the first cfg4 control, extrapolated."""
+    from oracle import bh_mps as ob
+    c = CFG4
+    so = ob.BHStepper(c["L"], c["d"] + 1, c["J"], c["tstep"], ob.TruncArgs(cutoff=c["cutoff"], maxm=c["maxm"]))
+    p = probs[0]
+    N = p.getN()
+    u = p.basis._ucurrent
+    conv = lambda h: ob.MPS(h.A, [np.asarray(x, dtype=np.int64) for x in h.q], 0, 2)
+    idx = [int(round(x)) for x in np.linspace(4, N - 5, 4)]
+    tf, tb, to = [], [], []
+    for i in idx:
+        a = conv(p.psi_t.get(i).download()); b = conv(p.xi_t.get(i).download())
+        t0 = time.perf_counter(); so.step(a.copy(), u[i], u[i + 1], True); tf.append(time.perf_counter() - t0)
+        t0 = time.perf_counter(); so.step(b.copy(), u[i], u[i - 1], False); tb.append(time.perf_counter() - t0)
+        t0 = time.perf_counter(); ob.overlap_K(b, a); to.append(time.perf_counter() - t0)
+    per_eval = (N - 1) * (np.mean(tf) + np.mean(tb)) + (N + 1) * np.mean(to)
+    return {"value": 1.0 / per_eval, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": "oracle port: 1 forward + 1 backward step + 1 MPO overlap at 4 slices of the first control, extrapolated to one evaluation "
+                      "(the CPU evaluates the seeds one after the other)", "fwd_step_s": float(np.mean(tf)), "bwd_step_s": float(np.mean(tb)),
+            "cpu_seconds": float(np.sum(tf) + np.sum(tb) + np.sum(to))}
+
+
+def cfg5_bench(oc, ctx, peak, with_cpu):
+    """BASELINE.json configs[4]: long chain BH L=50 Npart=50 d=5, chi=256, Cutoff=1e-10, SVD-bound stress on one GPU.  Bounded sample:
+    the Mott product state is quenched (steps of 5*tstep at U=2.5) until the largest bond reaches 256, then forward Trotter steps
+    and a BFGS-mode gradient (on-the-fly xi, src/OptimalControl.cpp:217-229) over a short horizon are timed; reported per step."""
+    c = CFG5
+    L, d = c["L"], c["d"]
+    D = d + 1
+    args = oc.Args("Cutoff=", c["cutoff"], "Maxm=", c["maxm"])
+    quench = oc.BH_tDMRG(oc.BoseHubbard(L, d), c["J"], 5 * c["tstep"], args, ctx=ctx)
+    st = oc.BH_tDMRG(oc.BoseHubbard(L, d), c["J"], c["tstep"], args, ctx=ctx)
+    A = []
+    for j in range(L):
+        a = np.zeros((1, D, 1), dtype=np.complex128)
+        a[0, 1, 0] = 1.0
+        A.append(a)
+    q = [np.array([b], dtype=np.int32) for b in range(L + 1)]
+    psi = quench.to_device(oc.IQMPS(A, q, 0, 2))
+    t0 = time.perf_counter()
+    nq = 0
+    while max(psi.bond_dims()) < c["maxm"] and nq < 400 and time.perf_counter() - t0 < 60.0:
+        quench.step(psi, 2.5, 2.5, True)
+        nq += 1
+    t_quench = time.perf_counter() - t0
+    dims = psi.bond_dims()
+    K = 5
+    st.step(psi, 2.5, 2.6, True)                       # warm (graph capture of the tstep stepper happens on reuse)
+    st.step(psi, 2.6, 2.7, True)
+    t0 = time.perf_counter()
+    for k in range(K):
+        st.step(psi, 2.7 + 0.1 * k, 2.8 + 0.1 * k, True)
+    ms_step = (time.perf_counter() - t0) / K * 1e3
+    # BFGS-mode gradient on a horizon of Nh points starting from the quenched state (target: the same state, so xi is as heavy as psi)
+    Nh = 6
+    u = list(np.linspace(3.2, 3.7, Nh))
+    h = psi.download()
+    pb = oc.OptimalControl(h, h, st, Nh, c["gamma"], True)
+    pb.getAnalyticGradient(u, True)
+    t0 = time.perf_counter()
+    g = pb.getAnalyticGradient(u, True)
+    cost = pb.getCost(u, False)
+    t_bfgs = time.perf_counter() - t0
+    Nt = int(c["T"] / c["tstep"] + 1)
+    out = {"workload": "cfg5: BH L=50 Npart=50 d=5 chi=256 Cutoff=1e-10; bounded sample at saturated bond dimensions: forward Trotter steps and "
+                       f"a BFGS-mode gradient over {Nh} time points", "quench_steps": nq, "quench_seconds": t_quench, "bond_dims_max": int(max(dims)),
+           "bonds_at_256": int(sum(1 for x in dims if x >= c["maxm"])), "ms_per_forward_step": ms_step,
+           "bfgs_gradient_ms_per_time_point": t_bfgs / Nh * 1e3, "unit": "ms",
+           "extrapolated_eval_s_Nt501": (Nt - 1) * ms_step * 1e-3 + Nt * t_bfgs / Nh,
+           "roofline": svd_roofline(ctx.lib, lambda: st.step(psi, 3.3, 3.4, True), peak)}
+    if with_cpu:
+        from oracle import bh_mps as ob
+        so = ob.BHStepper(L, D, c["J"], c["tstep"], ob.TruncArgs(cutoff=c["cutoff"], maxm=c["maxm"]))
+        hh = psi.download()
+        po = ob.MPS(hh.A, [np.asarray(x, dtype=np.int64) for x in hh.q], 0, 2)
+        t0 = time.perf_counter()
+        so.step(po, 3.4, 3.5, True)
+        dtc = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": dtc * 1e3, "unit": "ms per forward step", "cores": os.cpu_count() or 1, "kind": "port",
+                               "sample": "oracle port, ONE forward Trotter step from the same saturated state"}
+    return out
+
 
 
 def hessian_bench(Nt, oc, ocd, st, psi_i, psi_f, world, rank, dev, torch):
@@ -492,6 +743,10 @@ def main():
     ap.add_argument("--seed", type=int, default=0, help="seed of the synthetic control")
     ap.add_argument("--distinct-seeds", action="store_true", help="N>1: rank r evaluates the control of seed r")
     ap.add_argument("--batch", type=int, default=6, help="additionally time this many independent controls in flight on one GPU")
+    ap.add_argument("--cfg1", type=int, default=1, help="1: add the cfg1 block (README input, GPU and CPU in full; N=1 only)")
+    ap.add_argument("--cfg5", type=int, default=1, help="1: add the cfg5 block (L=50 chi=256 bounded sample; N=1 only)")
+    ap.add_argument("--cfg4-seeds", type=int, default=8, help="controls per GPU of the cfg4 block (L=30 chi=150 batched seeds); 0 = off")
+    ap.add_argument("--cfg4-inflight", type=int, default=4, help="cfg4 controls evaluated concurrently per GPU (21 GB of slice stores each)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -52,6 +52,8 @@ int ocmps_profile_read(double* out4);
 int ocmps_ctx_create(int device, ocmps_ctx** out);
 int ocmps_ctx_destroy(ocmps_ctx* ctx);
 int ocmps_ctx_synchronize(ocmps_ctx* ctx);
+/* frees the idle per-chain workspaces the library keeps between calls (they are re-created on demand) */
+int ocmps_ctx_trim(ocmps_ctx* ctx);
 /* measurement aid (bench.py): a pair of CUDA events on the library's own stream; stop returns the milliseconds between them */
 int ocmps_timer_start(ocmps_ctx* ctx);
 int ocmps_timer_stop(ocmps_ctx* ctx, double* ms);

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libocmps.so")
 # every symbol include/ocmps.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "ocmps_last_error", "ocmps_version", "ocmps_launch_count", "ocmps_profile_enable", "ocmps_profile_read",
-    "ocmps_ctx_create", "ocmps_ctx_destroy", "ocmps_ctx_synchronize", "ocmps_timer_start", "ocmps_timer_stop",
+    "ocmps_ctx_create", "ocmps_ctx_destroy", "ocmps_ctx_synchronize", "ocmps_ctx_trim", "ocmps_timer_start", "ocmps_timer_stop",
     "ocmps_mps_create", "ocmps_mps_destroy", "ocmps_mps_upload", "ocmps_mps_sizes", "ocmps_mps_download",
     "ocmps_mps_bond_dims", "ocmps_mps_copy", "ocmps_mps_norm", "ocmps_overlap", "ocmps_overlap_K",
     "ocmps_stepper_create", "ocmps_stepper_destroy", "ocmps_stepper_set_tstep", "ocmps_stepper_get_tstep",
@@ -53,6 +53,7 @@ def load():
         "ocmps_ctx_create": (i, [i, pvp]),
         "ocmps_ctx_destroy": (i, [vp]),
         "ocmps_ctx_synchronize": (i, [vp]),
+        "ocmps_ctx_trim": (i, [vp]),
         "ocmps_timer_start": (i, [vp]),
         "ocmps_timer_stop": (i, [vp, pd]),
         "ocmps_mps_create": (i, [vp, i, i, i, pvp]),

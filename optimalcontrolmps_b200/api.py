@@ -54,6 +54,10 @@ class Context:
     def synchronize(self):
         _lib.check(self.lib.ocmps_ctx_synchronize(self.h))
 
+    def trim(self):
+        """Frees the idle per-chain workspaces (scratch, Hessian rings, step graphs) the library keeps between calls."""
+        _lib.check(self.lib.ocmps_ctx_trim(self.h))
+
 
 class BoseHubbard:
     """``BoseHubbard(N, d)`` site set: N sites with occupations 0..d (local dimension d+1)."""

@@ -307,9 +307,8 @@ void free_ws(Workspace* w) {
   if (w->rowstore) { cudaFree(w->rowstore->data); cudaFree(w->rowstore->dims); cudaFree(w->rowstore->q); delete w->rowstore; }
   cudaFree(w->E[0]); cudaFree(w->E[1]); cudaFree(w->T); cudaFree(w->odescs); cudaFree(w->d_out);
   cudaFree(w->d_status); cudaFree(w->d_div);
-  if (w->work) w->work->ctx = nullptr;      // (the context is going away: no graph bookkeeping)
+  if (w->work) w->work->ctx = nullptr;      // (owned by the workspace, whose graphs are gone with it: no bookkeeping)
   if (w->big) w->big->ctx = nullptr;
-  if (w->psiH) w->psiH->ctx = nullptr;
   free_mps(w->work); free_mps(w->big);
   if (w->bigws) free_ws(w->bigws);
   if (w->stream) cudaStreamDestroy(w->stream);
@@ -903,6 +902,8 @@ int apply_K_async(ocmps_stepper* st, Workspace* ws, ocmps_mps* in, ocmps_mps* ou
     if (rc) return rc;
     rc = alloc_ws(st->ctx, L, D, cap2, false, &ws->bigws);
     if (rc) return rc;
+    ws->bigws->db.status = ws->d_status;            // what its kernels flag is reported with the owning workspace
+    ws->bigws->db2.status = ws->d_status;
   }
   ocmps_mps* big = ws->big;
   Workspace* bw = ws->bigws;
@@ -1019,6 +1020,22 @@ int ocmps_timer_stop(ocmps_ctx* ctx, double* ms) {
   float f = 0.f;
   CK(cudaEventElapsedTime(&f, ctx->t0, ctx->t1));
   *ms = (double)f;
+  return OCMPS_OK;
+}
+
+// Releases the idle workspaces of the pool (streams, scratch, Hessian rings, step graphs).  They are re-created on demand;
+// a long-lived process calls this between workloads of different shapes (bench.py does, before the chi=150 batch).
+int ocmps_ctx_trim(ocmps_ctx* ctx) {
+  if (!ctx) return fail(OCMPS_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(ctx->dev));
+  std::vector<Workspace*> idle;
+  {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    std::vector<Workspace*> keep;
+    for (Workspace* w : ctx->pool) (w->busy ? keep : idle).push_back(w);
+    ctx->pool.swap(keep);
+  }
+  for (Workspace* w : idle) { cudaStreamSynchronize(w->stream); if (w->ovl) cudaStreamSynchronize(w->ovl); free_ws(w); }
   return OCMPS_OK;
 }
 

@@ -126,3 +126,19 @@ def test_larger_charges_after_graph_capture_are_not_truncated_away():
         got = to_oracle(dev.download())
         assert got.bond_dims() == want.bond_dims()
         assert abs(abs(ob.overlap(want, got)) - 1.0) < 1e-10
+
+
+def test_trim_releases_idle_workspaces_and_everything_still_works():
+    """ocmps_ctx_trim frees the pooled per-chain workspaces (including the Hessian buffers); later calls re-create them and give
+    the same numbers."""
+    oc, z, st, init, target, N, gamma = _setup("golden_L6_maxm.npz")
+    u = list(z["u"])
+    p = oc.OptimalControl(to_host(target), to_host(init), st, N, gamma)
+    H0 = np.array(p.getHessian(u, True))
+    c0 = p.getCost(u, False)
+    st.ctx.trim()
+    st.ctx.trim()                               # idempotent
+    H1 = np.array(p.getHessian(u, True))
+    assert np.array_equal(H0, H1)
+    assert p.getCost(u, True) == c0
+    assert np.max(np.abs(H0 - z["hessian"])) / np.max(np.abs(z["hessian"])) < 1e-6

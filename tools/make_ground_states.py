@@ -23,13 +23,21 @@ def main():
     configs = [  # (L, d, Npart, maxm, cutoff)
         (20, 5, 20, 100, 1e-8),     # cfg2 / cfg3
         (8, 4, 8, 40, 1e-9),        # mid-size test problem
+        (5, 4, 5, 0, 0.0),          # cfg1 (README input): exact diagonalisation
+        (30, 5, 30, 150, 1e-8),     # cfg4 (batched seeds)
     ]
+    only = [int(x) for x in sys.argv[1:]]          # optional: chain lengths to (re)generate
     for (L, d, Np, maxm, cutoff) in configs:
+        if only and L not in only:
+            continue
         for U in (2.5, 50.0):
             t0 = time.time()
-            psi = og.ground_state_dmrg(L, d + 1, Np, 1.0, U, maxm_schedule=(10, 20, 50, maxm), cutoff=cutoff, nsweeps=10)
+            if maxm == 0:
+                psi = og.ground_state_ed(L, d + 1, Np, 1.0, U)
+            else:
+                psi = og.ground_state_dmrg(L, d + 1, Np, 1.0, U, maxm_schedule=(10, 20, 50, maxm), cutoff=cutoff, nsweeps=10)
             e = og.mps_energy(psi, 1.0, U)
-            print(f"L={L} d={d} U={U}: E={e:.10f} dims={psi.bond_dims()} ({time.time() - t0:.1f}s)")
+            print(f"L={L} d={d} U={U}: E={e:.10f} dims={psi.bond_dims()} ({time.time() - t0:.1f}s)", flush=True)
             save(f"bh_L{L}_d{d}_N{Np}_U{U:g}.npz", psi, [L, d, Np, 1.0, U, maxm, cutoff, e])
 
 
