@@ -96,6 +96,25 @@ int main(int argc, char** argv) {
     check(std::fabs(tot - tot0) < 1e-10 && std::fabs(tot0 - std::round(tot0)) < 1e-8, "expectationValues: particle number conserved", std::fabs(tot - tot0));
     check(dev < 1e-11, "expectationValues: <NN> = <N(N-1)> + <N>", dev);
     check(std::abs(expectationValue(sites, psi, "N", 2) - nj[1]) < 1e-14, "expectationValue(site 2)", 0.0);
+    {   // two-point functions: trace of <Adag_i A_j> is the particle number, its diagonal equals <N_i>, and the largest eigenvalue
+        // of the one-body density matrix lies between the largest occupation and the particle number
+      auto rho = correlationMatrix(sites, psi, "Adag", "A");
+      double tr = 0.0, dmax = 0.0, herm = 0.0, nmax = 0.0;
+      for (size_t i = 0; i < rho.size(); ++i) {
+        tr += rho[i][i].real();
+        dmax = std::max(dmax, std::fabs(rho[i][i].real() - nj[i].real()));
+        nmax = std::max(nmax, nj[i].real());
+        for (size_t j = 0; j < rho.size(); ++j) herm = std::max(herm, std::abs(rho[i][j] - std::conj(rho[j][i])));
+      }
+      check(std::fabs(tr - tot) < 1e-10 && dmax < 1e-11 && herm < 1e-14, "correlationMatrix(Adag, A): trace, diagonal, hermiticity", std::fabs(tr - tot));
+      const double lam = correlationTerm(sites, psi, "Adag", "A");
+      check(lam >= nmax - 1e-10 && lam <= tot + 1e-10, "correlationTerm(Adag, A) within [max n_i, N]", lam);
+      const Cplx c13 = correlationFunction(sites, psi, "Adag", 1, "A", 3);
+      check(std::abs(c13 - rho[0][2]) < 1e-14, "correlationFunction(Adag,1,A,3) = rho[1][3]", std::abs(c13));
+      const Cplx aad = correlationFunction(sites, psi, "A", 2, "Adag", 2), ada = correlationFunction(sites, psi, "Adag", 2, "A", 2);
+      const double comm = (aad - ada).real();        // [A, Adag] = 1 below the occupation cut-off, -d on the top level
+      check(comm <= 1.0 + 1e-12 && comm > 0.9 && std::fabs((aad - ada).imag()) < 1e-13, "same site: <A Adag> - <Adag A> = 1 - (d+1) P(n=d)", comm);
+    }
     auto SvN = entanglementEntropy(sites, psi);
     bool sok = (int)SvN.size() == L - 1;
     for (double x : SvN) sok = sok && x > -1e-12 && x < std::log((double)cap) + 1e-9;

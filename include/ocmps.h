@@ -124,6 +124,13 @@ int ocmps_store_divT(ocmps_store* xi_store, ocmps_store* psi_store, int Nt, doub
  * receives <psi_z|psi_z> as seen from every site, count*L values that all equal the norm when that holds. */
 int ocmps_store_site_expectations(ocmps_store* store, int first, int count, const double* op_diag, int nops,
                                   double* out /* count*L*nops */, double* norm2 /* count*L or NULL */);
+/* Two-point functions on a resident slice (include/correlations.hpp:10-55 correlationFunction, :57-80 correlationMatrix; used per
+ * slice at main/AnalyzeQuench.cpp:143-144): out[z] = <psi| O_a(site_a) O_b(site_b) |psi> for `nentries` entries of four ints
+ * (site_a, op_a, site_b, op_b): sites 0-based and distinct, op_x an index into op_table (nops real D x D matrices, row-major
+ * O[t*D + s] = <t|O|s>, e.g. A: <j-1|A|j> = sqrt(j), include/BH_sites.h:129-171); site_b = -1 for a single operator (the caller
+ * multiplies two operators that sit on the same site, :17-24).  Not divided by the norm.  Any gauge. */
+int ocmps_store_correlations(ocmps_store* store, int slot, const double* op_table, int nops, const int* entries, int nentries,
+                             double* out /* 2*nentries */);
 /* Entanglement entropy of every bond (include/correlations.hpp:119-148: psi.position(i), SVD of the two-site wavefunction,
  * S = -sum_{p > 1e-12} p ln p over the density-matrix eigenvalues): out[z*(L-1) + (i-1)] for bond i = 1..L-1 of the slices
  * first..first+count-1.  Works on a copy (the store is not modified); slices must have their centre at site 1. */

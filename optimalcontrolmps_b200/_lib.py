@@ -22,7 +22,7 @@ SYMBOLS = [
     "ocmps_store_create", "ocmps_store_destroy", "ocmps_store_get", "ocmps_store_put", "ocmps_store_bond_dims",
     "ocmps_forward_sweep", "ocmps_backward_sweep", "ocmps_sweep_pair", "ocmps_sweep_batch", "ocmps_backward_sweep_divT",
     "ocmps_store_overlaps", "ocmps_store_divT", "ocmps_store_apply_K", "ocmps_hessian_rows", "ocmps_hessian_eval",
-    "ocmps_store_site_expectations", "ocmps_store_entanglement_entropy",
+    "ocmps_store_site_expectations", "ocmps_store_entanglement_entropy", "ocmps_store_correlations",
 ]
 
 
@@ -91,6 +91,7 @@ def load():
         "ocmps_hessian_eval": (i, [vp, vp, vp, pd, i, vp, vp, vp, pi, i, i, i, i, pd, pd, pd, pd]),
         "ocmps_store_site_expectations": (i, [vp, i, i, pd, i, pd, pd]),
         "ocmps_store_entanglement_entropy": (i, [vp, i, i, pd]),
+        "ocmps_store_correlations": (i, [vp, i, pd, i, pi, i, pd]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -219,6 +219,33 @@ class SliceStore:
         _lib.check(self.ctx.lib.ocmps_store_entanglement_entropy(self.h, first, count, _pd(out)))
         return out
 
+    # ---- two-point functions (include/correlations.hpp:10-97), one batched transfer-matrix pass per call ----
+    def correlationFunction(self, slot: int, opname1: str, i: int, opname2: str, j: int) -> complex:
+        """``correlationFunction(sites, psi, opname1, i, opname2, j)`` for the slice ``slot``: <psi| Op1_i Op2_j |psi>, sites
+        1-based.  (For i > j the reference swaps the sites but not the operators, which ITensor then cannot contract; here
+        the value is simply the expectation of Op1 at site i and Op2 at site j in either order.)"""
+        return complex(_correlation_entries(self, slot, [(opname1, i, opname2, j)])[0])
+
+    def correlationMatrix(self, slot: int, opname1: str, opname2: str) -> np.ndarray:
+        """``correlationMatrix`` (:57-80): rho[i, j] = <Op1_i Op2_j> for i <= j, rho[j, i] = conj(rho[i, j]).  The diagonal is
+        real (the reference takes ``.real()`` of the same-site value, :24)."""
+        L = self.L
+        req = [(opname1, i, opname2, j) for i in range(1, L + 1) for j in range(i, L + 1)]
+        vals = _correlation_entries(self, slot, req)
+        rho = np.zeros((L, L), dtype=np.complex128)
+        for (o1, i, o2, j), v in zip(req, vals):
+            if i == j:
+                rho[i - 1, i - 1] = v.real
+            else:
+                rho[i - 1, j - 1] = v
+                rho[j - 1, i - 1] = np.conj(v)
+        return rho
+
+    def correlationTerm(self, slot: int, opname1: str, opname2: str) -> float:
+        """``correlationTerm`` (:82-97): largest eigenvalue of the correlation matrix (an L x L Hermitian matrix, diagonalised
+        on the host like every other O(L^3) post-processing step of the reference)."""
+        return float(np.linalg.eigvalsh(self.correlationMatrix(slot, opname1, opname2))[-1])
+
     # site operators of include/BH_sites.h:129-171 that are diagonal in the boson number
     SITE_OPS = {"N": lambda n: n, "N(N-1)": lambda n: n * (n - 1.0), "NN": lambda n: n * n, "Id": lambda n: 1.0 + 0.0 * n}
 
@@ -236,6 +263,57 @@ class SliceStore:
         nrm = np.zeros((count, self.L))
         _lib.check(self.ctx.lib.ocmps_store_site_expectations(self.h, first, count, _pd(diags), len(opnames), _pd(out), _pd(nrm)))
         return (out, nrm) if return_norm else out
+
+
+def site_operator(opname: str, D: int) -> np.ndarray:
+    """<t|Op|s> of the site operators of include/BH_sites.h:129-171 as a real D x D matrix ("Id" is the true identity, which
+    is what ITensor's SiteSet hands out for that name)."""
+    n = np.arange(D, dtype=float)
+    if opname == "N":
+        return np.diag(n)
+    if opname == "N(N-1)":
+        return np.diag(n * (n - 1.0))
+    if opname == "NN":
+        return np.diag(n * n)
+    if opname == "Id":
+        return np.eye(D)
+    A = np.zeros((D, D))
+    for j in range(1, D):
+        A[j - 1, j] = math.sqrt(j)                     # <j-1|A|j> = sqrt(j)   (:136-141)
+    if opname == "A":
+        return A
+    if opname == "Adag":
+        return A.T.copy()                              # <j|Adag|j-1> = sqrt(j) (:143-148)
+    raise ValueError(f"site operator {opname!r} not recognized")
+
+
+def _correlation_entries(store: "SliceStore", slot: int, requests):
+    """requests: list of (opname1, i, opname2, j), sites 1-based like the reference.  Returns complex values
+    <psi| Op1_i Op2_j |psi> (include/correlations.hpp:10-55; for i == j the product Op1.Op2 on that site, :17-24)."""
+    D = store.D
+    table, index = [], {}
+
+    def op_id(mat):
+        key = mat.tobytes()
+        if key not in index:
+            index[key] = len(table)
+            table.append(mat)
+        return index[key]
+
+    entries = []
+    for (o1, i, o2, j) in requests:
+        if not (1 <= i <= store.L and 1 <= j <= store.L):
+            raise ValueError("site out of range")
+        m1, m2 = site_operator(o1, D), site_operator(o2, D)
+        if i == j:
+            entries.append((i - 1, op_id(m1 @ m2), -1, 0))
+        else:
+            entries.append((i - 1, op_id(m1), j - 1, op_id(m2)))
+    ops = np.ascontiguousarray(np.stack(table), dtype=np.float64)
+    ent = np.ascontiguousarray(np.array(entries, dtype=np.int32))
+    out = np.zeros(2 * len(entries))
+    _lib.check(store.ctx.lib.ocmps_store_correlations(store.h, int(slot), _pd(ops), len(table), _pi(ent), len(entries), _pd(out)))
+    return out.view(np.complex128).copy()
 
 
 def overlapC(a: DeviceMPS, b: DeviceMPS) -> complex:

@@ -329,6 +329,32 @@ __global__ void overlap_kfix_kernel(cplx* T, long long t_stride, const GemmDesc*
   }
 }
 
+// Site operator on the physical index of T, in place, for the batch entries that have one at this site (sel[z] >= 0):
+// T'[l][t][r] = sum_s O[t][s] T[l][s][r] with O = op_table[sel[z]] (D x D, real, row-major O[t][s] = <t|O|s>; the operators of
+// include/BH_sites.h:129-171 -- N, A, Adag, N(N-1), NN, Id -- and their products).  One thread per (l, r).
+__global__ void overlap_site_op_kernel(cplx* T, long long t_stride, const GemmDesc* descs, int D, const double* __restrict__ op_table,
+                                       const int* __restrict__ sel) {
+  const int z = blockIdx.y;
+  const int op = sel[z];
+  if (op < 0) return;
+  const GemmDesc g = descs[z];
+  const int aL = g.M, N = g.N, bR = N / D;
+  const double* O = op_table + (size_t)op * D * D;
+  cplx* Tz = T + z * t_stride;
+  const long long total = (long long)aL * bR;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int l = (int)(e / bR), r = (int)(e % bR);
+    cplx* col = Tz + (long long)l * N + r;
+    cplx v[OCMPS_MAX_D];
+    for (int sI = 0; sI < D; ++sI) v[sI] = col[(long long)sI * bR];
+    for (int t = 0; t < D; ++t) {
+      double ar = 0.0, ai = 0.0;
+      for (int sI = 0; sI < D; ++sI) { const double o = O[t * D + sI]; ar += o * v[sI].x; ai += o * v[sI].y; }
+      col[(long long)t * bR] = make_double2(ar, ai);
+    }
+  }
+}
+
 __global__ void overlap_final_kernel(const cplx* E, long long e_stride, int batch, int withK, cplx* out) {
   const int z = blockIdx.x * blockDim.x + threadIdx.x;
   if (z >= batch) return;
@@ -447,6 +473,13 @@ void launch_overlap_init(cplx* E, long long e_stride, int batch, int withK, cuda
 void launch_overlap_kfix(cplx* T, long long t_stride, const GemmDesc* descs, int batch, int D, int max_elems, cudaStream_t s) {
   dim3 grid(grid_for(max_elems, 256, 32), batch);
   overlap_kfix_kernel<<<grid, 256, 0, s>>>(T, t_stride, descs, D);
+}
+void launch_overlap_site_op(cplx* T, long long t_stride, const GemmDesc* descs, int batch, int D, const double* op_table, const int* sel,
+                            int max_elems, cudaStream_t s) {
+  int gx = (max_elems + 255) / 256;
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  overlap_site_op_kernel<<<dim3(gx, batch), 256, 0, s>>>(T, t_stride, descs, D, op_table, sel);
 }
 void launch_overlap_final(const cplx* E, long long e_stride, int batch, int withK, cplx* out, cudaStream_t s) {
   overlap_final_kernel<<<(batch + 63) / 64, 64, 0, s>>>(E, e_stride, batch, withK, out);

@@ -1587,6 +1587,76 @@ int ocmps_store_site_expectations(ocmps_store* store, int first, int count, cons
   return OCMPS_OK;
 }
 
+// Two-point functions on a resident slice (include/correlations.hpp:10-55 correlationFunction, :57-80 correlationMatrix):
+// out[z] = <psi| O_a(site_a) O_b(site_b) |psi> for `nentries` entries (site_a, op_a, site_b, op_b), sites 0-based, op_x an
+// index into `op_table` (nops real D x D matrices <t|O|s>), site_b = -1 for a single operator.  All entries go through ONE
+// batched pass of the <psi|psi> transfer-matrix chain with the operators applied to the physical index at their sites;
+// number-changing operators (A, Adag) are fine, the intermediate transfer matrices then connect charge q with q +- 1.
+// No gauge is assumed (the chain runs over all L sites), not divided by the norm (like the reference).
+int ocmps_store_correlations(ocmps_store* store, int slot, const double* op_table, int nops, const int* entries, int nentries,
+                             double* out) {
+  if (!store || !op_table || !entries || !out || nops < 1 || nentries < 1 || slot < 0 || slot >= store->nslots)
+    return fail(OCMPS_ERR_INVALID, "bad argument");
+  ocmps_ctx* ctx = store->ctx;
+  const Layout& lay = store->lay;
+  const int L = lay.L, D = lay.D;
+  for (int z = 0; z < nentries; ++z) {
+    const int* e = entries + 4 * z;
+    if (e[0] < 0 || e[0] >= L || e[1] < 0 || e[1] >= nops || e[2] >= L || (e[2] >= 0 && (e[3] < 0 || e[3] >= nops)) || e[2] == e[0])
+      return fail(OCMPS_ERR_INVALID, "correlations: entry out of range (two operators on one site must be multiplied by the caller)");
+  }
+  CK(cudaSetDevice(ctx->dev));
+  WsLease lease;
+  int rc = lease.acquire(ctx, L, D, lay.cap, 1);
+  if (rc) return rc;
+  Workspace* ws = lease[0];
+  cudaStream_t s = ws->stream;
+  const int chunk = 128;
+  double* d_ops = nullptr;
+  int* d_sel = nullptr;
+  CK(cudaMalloc(&d_ops, sizeof(double) * (size_t)nops * D * D));
+  CK(cudaMalloc(&d_sel, sizeof(int) * (size_t)L * chunk));
+  CK(cudaMemcpy(d_ops, op_table, sizeof(double) * (size_t)nops * D * D, cudaMemcpyHostToDevice));
+  // every batch entry reads the same slice: strides 0
+  OvlSide side = side_of_store(store, slot);
+  side.slot_stride = 0;
+  side.dims_stride = 0;
+  side.base = store->data + (size_t)slot * lay.total;
+  side.dims = store->dims + (size_t)slot * (L + 1);
+  side.slot0 = 0;
+  std::vector<int> h_sel((size_t)L * chunk);
+  for (int z0 = 0; z0 < nentries && !rc; z0 += chunk) {
+    const int nb = std::min(chunk, nentries - z0);
+    rc = ensure_overlap_bufs(ws, nb, lay.cap, lay.cap);
+    if (rc) break;
+    for (int j = 0; j < L; ++j)
+      for (int z = 0; z < nb; ++z) {
+        const int* e = entries + 4 * (z0 + z);
+        h_sel[(size_t)j * chunk + z] = e[0] == j ? e[1] : (e[2] == j ? e[3] : -1);
+      }
+    if (cudaMemcpyAsync(d_sel, h_sel.data(), sizeof(int) * h_sel.size(), cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = fail(OCMPS_ERR_CUDA, "copy failed"); break; }
+    launch_overlap_init(ws->E[0], ws->e_stride, nb, 0, s);
+    int cur = 0;
+    for (int j = 0; j < L; ++j) {
+      launch_overlap_plan(ws->odescs, side, side, j, nb, D, 0, ws->E[cur], ws->E[1 - cur], ws->T, ws->e_stride, ws->t_stride, s);
+      launch_zgemm(ws->odescs, nb, lay.capb[j], D * lay.capb[j + 1], s);
+      launch_overlap_site_op(ws->T, ws->t_stride, ws->odescs, nb, D, d_ops, d_sel + (size_t)j * chunk, lay.capb[j] * lay.capb[j + 1], s);
+      launch_zgemm(ws->odescs + nb, nb, lay.capb[j + 1], lay.capb[j + 1], s);
+      cur = 1 - cur;
+      g_ocmps_launches += 4;
+    }
+    launch_overlap_final(ws->E[cur], ws->e_stride, nb, 0, ws->d_out, s);
+    g_ocmps_launches += 2;
+    if (cudaMemcpyAsync(out + 2 * z0, ws->d_out, sizeof(cplx) * nb, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+      rc = fail(OCMPS_ERR_CUDA, "correlations: copy failed");
+  }
+  cudaStreamSynchronize(s);
+  cudaFree(d_ops); cudaFree(d_sel);
+  if (rc) return rc;
+  return lease.finish();
+}
+
 // Entanglement entropy of every bond of the slices first .. first+count-1 (include/correlations.hpp:119-148:
 // psi.position(i), SVD of the two-site wavefunction, S = -sum_{p>1e-12} p ln p over the density-matrix eigenvalues).
 // The orthogonality centre of a copy of the slice is moved from site 1 to site L with the engine's own gauge moves;

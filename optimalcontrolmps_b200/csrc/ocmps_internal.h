@@ -164,6 +164,8 @@ constexpr int OCMPS_EXPECT_MAX_OPS = 8;   // site operators per call of the expe
 void launch_overlap_local_expect(const GemmDesc* descs, const OvlSide& bra, int site, int batch, int D, const double* ops, int nops,
                                  double* out, int L, cudaStream_t s);
 void launch_overlap_kfix(cplx* T, long long t_stride, const GemmDesc* descs, int batch, int D, int max_elems, cudaStream_t s);
+void launch_overlap_site_op(cplx* T, long long t_stride, const GemmDesc* descs, int batch, int D, const double* op_table, const int* sel,
+                            int max_elems, cudaStream_t s);
 void launch_overlap_final(const cplx* E, long long e_stride, int batch, int withK, cplx* out, cudaStream_t s);
 
 // K|psi>: builds the bond-dimension-2chi tensors

@@ -42,3 +42,42 @@ def entanglement_entropy(psi):
         p = p[p > 1e-12]
         out[i - 1] = float(-(p * np.log(p)).sum())
     return out
+
+
+def correlation_function(psi, op1, i, op2, j):
+    """<psi| Op1_i Op2_j |psi>, sites 1-based, operators as D x D matrices <t|O|s> (include/correlations.hpp:10-55).
+    Follows the reference's contraction: for i == j the product Op1.Op2 on that site (:17-24, the reference returns its real
+    part); for i != j the transfer-matrix chain between the two sites (:37-52) -- here with the full left and right
+    environments instead of a gauge move, which gives the same number in any gauge."""
+    A = psi.A
+    L = len(A)
+    D = A[0].shape[1]
+    ops = {}
+    if i == j:
+        ops[i - 1] = np.asarray(op1, dtype=float) @ np.asarray(op2, dtype=float)
+    else:
+        ops[i - 1] = np.asarray(op1, dtype=float)
+        ops[j - 1] = np.asarray(op2, dtype=float)
+    E = np.ones((1, 1), dtype=complex)
+    for k in range(L):
+        O = ops.get(k, np.eye(D))
+        E = np.einsum("xy,xta,ts,ysb->ab", E, A[k].conj(), O, A[k])
+    return complex(E[0, 0])
+
+
+def correlation_matrix(psi, op1, op2):
+    """include/correlations.hpp:57-80."""
+    L = len(psi.A)
+    rho = np.zeros((L, L), dtype=complex)
+    for i in range(1, L + 1):
+        rho[i - 1, i - 1] = correlation_function(psi, op1, i, op2, i).real
+        for j in range(i + 1, L + 1):
+            c = correlation_function(psi, op1, i, op2, j)
+            rho[i - 1, j - 1] = c
+            rho[j - 1, i - 1] = np.conj(c)
+    return rho
+
+
+def correlation_term(psi, op1, op2):
+    """Largest eigenvalue of the correlation matrix (include/correlations.hpp:82-97)."""
+    return float(np.linalg.eigvalsh(correlation_matrix(psi, op1, op2))[-1])

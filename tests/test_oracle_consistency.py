@@ -245,3 +245,32 @@ def test_entropy_restatement_on_exact_states():
         p = np.linalg.svd(vec.reshape(D ** i, D ** (L - i)), compute_uv=False) ** 2
         p = p[p > 1e-12]
         assert abs(got[i - 1] + (p * np.log(p)).sum()) < 1e-12
+
+
+def test_correlation_function_restatement_against_dense_state_vector():
+    """oracle.observables.correlation_function (include/correlations.hpp:10-55) against brute-force state-vector arithmetic."""
+    from conftest import random_symmetric_mps
+    from oracle import observables as oo
+    from optimalcontrolmps_b200.api import site_operator
+    L, D, Np = 4, 4, 4
+    psi = random_symmetric_mps(L, D, Np, 8, 3)
+    v = psi.to_dense()
+
+    def dense(o1, i, o2, j):
+        ops = [np.eye(D)] * L
+        if i == j:
+            ops[i - 1] = o1 @ o2
+        else:
+            ops[i - 1], ops[j - 1] = o1, o2
+        w = v
+        for k, O in enumerate(ops):
+            w = np.moveaxis(np.tensordot(O, w, axes=(1, k)), 0, k)
+        return np.vdot(v, w)
+
+    for a, b in (("Adag", "A"), ("N", "N"), ("A", "Adag"), ("Id", "N(N-1)")):
+        o1, o2 = site_operator(a, D), site_operator(b, D)
+        for i in range(1, L + 1):
+            for j in range(i, L + 1):
+                assert abs(oo.correlation_function(psi, o1, i, o2, j) - dense(o1, i, o2, j)) < 1e-12
+    rho = oo.correlation_matrix(psi, site_operator("Adag", D), site_operator("A", D))
+    assert abs(np.trace(rho).real - Np) < 1e-12 and np.max(np.abs(rho - rho.conj().T)) < 1e-14
