@@ -13,6 +13,7 @@
 #include "correlations.hpp"
 #include "BH_tDMRG.hpp"
 #include "ControlBasisFactory.hpp"
+#include "InitializeState.hpp"
 #include "OptimalControl.hpp"
 
 static std::ifstream in;
@@ -151,6 +152,15 @@ int main(int argc, char** argv) {
   const Cplx k1 = overlapC(psi, kpsi), k2 = overlapC(psi, stepper.propagatorDeriv(u[0]), psi);
   check(std::abs(k1 - k2) < 5e-3 * std::abs(k2), "<psi|K psi> ~ <psi|K|psi> (up to the Maxm truncation)", std::abs(k1 - k2));
 
+  {   // InitializeState (include/InitializeState.hpp): Mott-side ground state on the device; N bosons, energy below the product state's
+    IQMPS gs = InitializeState(sites, L, J, ce, maxm > 0 ? maxm : cap, 1E-9);
+    auto n = expectationValues(sites, gs, "N");
+    double totn = 0.0;
+    for (auto& x : n) totn += x.real();
+    double hop = 0.0;
+    for (int i = 1; i < L; ++i) hop += correlationFunction(sites, gs, "Adag", i, "A", i + 1).real();
+    check(std::fabs(totn - L) < 1e-9 && std::fabs(norm(gs) - 1.0) < 1e-12 && hop > 0.0, "InitializeState: particle number, norm, kinetic energy", hop);
+  }
   // ---- GROUP ----
   auto u0 = SeedGenerator::linspace(cs, ce, N);
   auto basis = ControlBasisFactory::buildChoppedSineBasis(u0, tstep, T, M);

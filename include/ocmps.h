@@ -91,6 +91,14 @@ int ocmps_stepper_schedule(ocmps_stepper* st, int* quads, int cap);
 /* the two-site J gate exp(-+ i tstep h) as D^2 x D^2 interleaved complex (BondGate, src/BH_tDMRG.cpp:35-36) */
 int ocmps_stepper_gate(ocmps_stepper* st, int forward, double* out);
 
+/* InitializeState(sites, Npart, J, U[, maxBondDim, threshold]) (include/InitializeState.hpp:18-117): Bose-Hubbard ground state
+ * H = -J sum (a_i adag_{i+1} + h.c.) + U/2 sum n_i(n_i-1) with Npart <= L bosons, produced on the device by imaginary-time evolution
+ * with the Trotter-step kernels (the reference uses ITensor's DMRG; same start state :24-38, same bond-dimension schedule
+ * 10, 20, 50, maxm :52-54, cutoff = threshold).  tau_final <= 0 selects 2e-3.  `out` must have capacity >= maxm; it ends
+ * normalised with its orthogonality centre at site 1.  energy / steps may be NULL. */
+int ocmps_ground_state(ocmps_ctx* ctx, int L, int D, int Npart, double J, double U, int maxm, double cutoff, double tau_final,
+                       ocmps_mps* out, double* energy, int* steps);
+
 /* ---- resident slice stores and sweeps (OptimalControl::calcPsi / calcXi / calcDivT) ---- */
 int ocmps_store_create(ocmps_ctx* ctx, int L, int D, int chi_cap, int nslots, ocmps_store** out);
 int ocmps_store_destroy(ocmps_store* store);

@@ -12,9 +12,9 @@ import os as _os
 # before anything in the process touches CUDA; a value the user has set is left alone.
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
-from .api import (Args, BH_tDMRG, BoseHubbard, Context, ControlBasis, ControlBasisFactory, DeviceMPS, IQMPS,
+from .api import (Args, BH_tDMRG, InitializeState, BoseHubbard, Context, ControlBasis, ControlBasisFactory, DeviceMPS, IQMPS,
                   OptimalControl, SeedGenerator, SliceStore, batch_cost_gradient, overlapC, overlapC_K, site_operator)
 from ._lib import OcmpsError, LIB_PATH
 
-__all__ = ["Args", "BH_tDMRG", "BoseHubbard", "Context", "ControlBasis", "ControlBasisFactory", "DeviceMPS", "IQMPS",
+__all__ = ["Args", "BH_tDMRG", "InitializeState", "BoseHubbard", "Context", "ControlBasis", "ControlBasisFactory", "DeviceMPS", "IQMPS",
            "OptimalControl", "SeedGenerator", "batch_cost_gradient", "SliceStore", "overlapC", "overlapC_K", "site_operator", "OcmpsError", "LIB_PATH"]

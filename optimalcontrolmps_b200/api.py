@@ -316,6 +316,22 @@ def _correlation_entries(store: "SliceStore", slot: int, requests):
     return out.view(np.complex128).copy()
 
 
+def InitializeState(sites: "BoseHubbard", Npart: int, J: float, U: float, maxBondDim: int = 200, threshold: float = 1e-9,
+                    tau_final: float = 0.0, ctx: Optional["Context"] = None, chi_cap: Optional[int] = None, return_info: bool = False):
+    """``InitializeState(sites, Npart, J, U[, maxBondDim, threshold])`` (include/InitializeState.hpp:18-117): Bose-Hubbard ground
+    state as a device-resident MPS.  The reference runs ITensor's DMRG (maxm 10, 20, 50, maxBondDim; cutoff = threshold); here
+    the engine's own Trotter-step kernels run in imaginary time with the same start state and bond-dimension schedule
+    (``ocmps_ground_state``).  Returns a DeviceMPS (``.download()`` gives the host container)."""
+    ctx = ctx or Context.default()
+    L, D = sites.N(), sites.D
+    cap = int(chi_cap or min(maxBondDim, D ** (L // 2)))
+    out = DeviceMPS(ctx, L, D, cap)
+    e, n = C.c_double(), C.c_int()
+    _lib.check(ctx.lib.ocmps_ground_state(ctx.h, L, D, int(Npart), float(J), float(U), min(int(maxBondDim), cap), float(threshold),
+                                          float(tau_final), out.h, C.byref(e), C.byref(n)))
+    return (out, e.value, n.value) if return_info else out
+
+
 def overlapC(a: DeviceMPS, b: DeviceMPS) -> complex:
     """<a|b>, first argument conjugated (ITensor ``overlapC``)."""
     out = np.zeros(2)

@@ -181,6 +181,7 @@ struct ocmps_stepper {
   std::vector<std::complex<double>> h_G[2];
   std::vector<Op> ops;
   long long serial = 0;      // unique id (graph cache key)
+  bool imag = false;         // imaginary-time evolution exp(-tau H) (ground-state generator): real gates, renormalised every step
 };
 
 namespace {
@@ -396,7 +397,8 @@ struct WsLease {
 // ------------------------------------------------------------------------------------------------
 typedef std::complex<double> zc;
 
-std::vector<zc> bond_gate(int D, double J, double tau) {
+// exp(factor * h) by ITensor BondGate's Horner recursion; factor = -i tau for real time, -tau for imaginary time
+std::vector<zc> bond_gate(int D, double J, double tau, bool imag = false) {
   const int n = D * D;
   std::vector<zc> h(n * n, 0.0), unit(n * n, 0.0), term, gate, x(n * n);
   // h[(t1,t2),(s1,s2)] = -J (A x Adag + Adag x A); <j-1|A|j> = sqrt(j)   (BH_sites.h:136-148)
@@ -406,7 +408,7 @@ std::vector<zc> bond_gate(int D, double J, double tau) {
     for (int s1 = 0; s1 < D; ++s1) for (int s2 = 0; s2 < D; ++s2)
       h[(t1 * D + t2) * n + s1 * D + s2] = -J * (Aop(t1, s1) * Adop(t2, s2) + Adop(t1, s1) * Aop(t2, s2));
   for (int i = 0; i < n; ++i) unit[i * n + i] = 1.0;
-  for (int i = 0; i < n * n; ++i) x[i] = h[i] * zc(0.0, -tau);
+  for (int i = 0; i < n * n; ++i) x[i] = h[i] * (imag ? zc(-tau, 0.0) : zc(0.0, -tau));
   term = x;
   gate = unit;
   std::vector<zc> tmp(n * n);
@@ -553,8 +555,13 @@ void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int c
   g_ocmps_launches += 5 + (need_global ? 1 : 0) + (long_rows ? 1 : 0);
 }
 
-void phases_of(int D, double U, double tstep, double* re, double* im) {
+void phases_of(int D, double U, double tstep, double* re, double* im, bool imag = false) {
   for (int n = 0; n < D; ++n) {
+    if (imag) {                     // imaginary time: exp(-1/4 U tau n(n-1)), the same half-step split of the on-site term
+      re[n] = std::exp(-0.25 * U * tstep * (double)n * (double)(n - 1));
+      im[n] = 0.0;
+      continue;
+    }
     const double ang = -0.25 * U * tstep * (double)n * (double)(n - 1);   // src/BH_tDMRG.cpp:87-88
     re[n] = std::cos(ang);
     im[n] = std::sin(ang);
@@ -691,8 +698,8 @@ void run_step_body(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, cudaStream_t 
 }
 
 void fill_step_params(ocmps_stepper* st, double from, double to, bool forward, ocmps_store* store, int slot, StepParams& hp) {
-  phases_of(st->D, forward ? from : -from, st->tstep, hp.u1r, hp.u1i);   // src/BH_tDMRG.cpp:116-123
-  phases_of(st->D, forward ? to : -to, st->tstep, hp.u2r, hp.u2i);
+  phases_of(st->D, forward ? from : -from, st->tstep, hp.u1r, hp.u1i, st->imag);   // src/BH_tDMRG.cpp:116-123
+  phases_of(st->D, forward ? to : -to, st->tstep, hp.u2r, hp.u2i, st->imag);
   hp.G = st->d_G[forward ? 0 : 1];
   hp.slot_data = nullptr; hp.slot_dims = nullptr; hp.slot_q = nullptr;
   if (store) {
@@ -1201,7 +1208,7 @@ int ocmps_stepper_set_tstep(ocmps_stepper* st, double tstep) {
   st->tstep = tstep;
   const int n = st->D * st->D;
   for (int dir = 0; dir < 2; ++dir) {
-    st->h_G[dir] = bond_gate(st->D, st->J, dir == 0 ? tstep : -tstep);
+    st->h_G[dir] = bond_gate(st->D, st->J, dir == 0 ? tstep : -tstep, st->imag);
     if (!st->d_G[dir]) CK(cudaMalloc(&st->d_G[dir], sizeof(cplx) * n * n));
     CK(cudaMemcpy(st->d_G[dir], st->h_G[dir].data(), sizeof(cplx) * n * n, cudaMemcpyHostToDevice));
   }
@@ -1655,6 +1662,107 @@ int ocmps_store_correlations(ocmps_store* store, int slot, const double* op_tabl
   cudaFree(d_ops); cudaFree(d_sel);
   if (rc) return rc;
   return lease.finish();
+}
+
+// Bose-Hubbard ground state on the device engine (the role of include/InitializeState.hpp:18-117 in the reference:
+// psi_init / psi_target of every main program and test come from it).  The reference runs ITensor's DMRG; here the SAME
+// Trotter-step kernels that do the real-time evolution run in imaginary time: gates exp(-tau h), on-site factors
+// exp(-tau U/4 n(n-1)), renormalisation after every truncation (which the step does anyway).  Start: the reference's
+// product state (one boson on each of the last Npart sites, :24-38).  tau is lowered in stages (0.1 -> tau_final) with the
+// reference's bond-dimension schedule 10, 20, 50, maxm (:52-54); a stage ends when the energy
+// <H> = -J sum <a+_i a_{i+1} + h.c.> + U/2 sum <n_i(n_i-1)> (two-point functions + site expectations on the device) has stopped
+// moving.  The fixed point of a first-order Trotter splitting differs from the true ground state by O(tau) in the state and
+// O(tau^2) in the energy; tau_final = 2e-3 gives energies good to ~1e-6 relative.  Result: normalised, centre at site 1.
+int ocmps_ground_state(ocmps_ctx* ctx, int L, int D, int Npart, double J, double U, int maxm, double cutoff, double tau_final,
+                       ocmps_mps* out, double* energy_out, int* steps_out) {
+  if (!ctx || !out) return fail(OCMPS_ERR_INVALID, "null argument");
+  if (L < 2 || Npart < 0 || Npart > L) return fail(OCMPS_ERR_INVALID, "ground_state: needs L >= 2 and 0 <= Npart <= L (the reference supports one boson per site at most in its initial guess)");
+  if (out->lay.L != L || out->lay.D != D) return fail(OCMPS_ERR_INVALID, "ground_state: output MPS has another shape");
+  if (maxm < 1) maxm = out->lay.cap;
+  if (maxm > out->lay.cap) return fail(OCMPS_ERR_CAPACITY, "ground_state: maxm exceeds the capacity of the output MPS");
+  if (!(tau_final > 0.0)) tau_final = 2e-3;
+  if (cutoff < 0.0) cutoff = 1e-9;
+  CK(cudaSetDevice(ctx->dev));
+  const int cap = out->lay.cap;
+  {   // product state |0..0 1..1>
+    std::vector<int> dims(L + 1, 1), q(L + 1, 0);
+    std::vector<double> t((size_t)2 * L * D, 0.0);
+    int tot = 0;
+    for (int j = 0; j < L; ++j) {
+      const int occ = j >= L - Npart ? 1 : 0;
+      t[((size_t)j * D + occ) * 2] = 1.0;
+      tot += occ;
+      q[j + 1] = tot;
+    }
+    int rc = ocmps_mps_upload(out, dims.data(), q.data(), t.data(), 0, 2);
+    if (rc) return rc;
+  }
+  ocmps_store* tmp = nullptr;
+  int rc = ocmps_store_create(ctx, L, D, cap, 1, &tmp);
+  if (rc) return rc;
+  // operator table: 0 = Adag, 1 = A; entries (i, Adag, i+1, A)
+  std::vector<double> ops((size_t)2 * D * D, 0.0);
+  for (int j = 1; j < D; ++j) { ops[(size_t)j * D + (j - 1)] = std::sqrt((double)j); ops[(size_t)D * D + (size_t)(j - 1) * D + j] = std::sqrt((double)j); }
+  std::vector<int> entries;
+  for (int i = 0; i + 1 < L; ++i) { entries.push_back(i); entries.push_back(0); entries.push_back(i + 1); entries.push_back(1); }
+  std::vector<double> corr((size_t)2 * (L - 1)), nn1(L), nrm(L), diag(D);
+  for (int n = 0; n < D; ++n) diag[n] = (double)n * (n - 1);
+  auto energy = [&](double& e) -> int {
+    int r = ocmps_store_put(tmp, 0, out);
+    if (!r) r = ocmps_store_correlations(tmp, 0, ops.data(), 2, entries.data(), L - 1, corr.data());
+    if (!r) r = ocmps_store_site_expectations(tmp, 0, 1, diag.data(), 1, nn1.data(), nrm.data());
+    if (r) return r;
+    double hop = 0.0, on = 0.0;
+    for (int i = 0; i + 1 < L; ++i) hop += corr[2 * i];
+    for (int j = 0; j < L; ++j) on += nn1[j];
+    e = (-2.0 * J * hop + 0.5 * U * on) / nrm[0];
+    return OCMPS_OK;
+  };
+  const int sched[4] = {10, 20, 50, maxm};
+  std::vector<double> taus;
+  for (double tau : {0.1, 0.05, 0.02, 0.01, 0.005, 0.002, 0.001, 0.0005, 0.0002, 0.0001})
+    if (tau > tau_final * 1.0001) taus.push_back(tau);
+  taus.push_back(tau_final);
+  int total_steps = 0;
+  double e_prev = 0.0, e = 0.0;
+  rc = energy(e_prev);
+  for (size_t sg = 0; sg < taus.size() && !rc; ++sg) {
+    const double tau = taus[sg];
+    const int mm = std::min(maxm, sched[std::min<size_t>(sg, 3)]);
+    ocmps_stepper* st = nullptr;
+    rc = ocmps_stepper_create(ctx, L, D, J, tau, cutoff, mm, cap, 0, &st);
+    if (rc) break;
+    st->imag = true;
+    rc = ocmps_stepper_set_tstep(st, tau);              // rebuilds the gates as exp(-tau h)
+    const int check = 10, max_steps = 4000;
+    const double tol = 1e-10 * std::max(1.0, tau / tau_final);
+    int quiet = 0;
+    for (int k = 0; k < max_steps && !rc; k += check) {
+      {
+        WsLease lease;
+        rc = lease.acquire(ctx, L, D, cap, 1);
+        if (rc) break;
+        Workspace* ws = lease[0];
+        for (int i = 0; i < check && !rc; ++i) rc = step_enqueue(st, out, ws, U, U, true, nullptr, 0, ws->stream);
+        if (rc) { cudaStreamSynchronize(ws->stream); break; }
+        rc = lease.finish();
+        if (rc) break;
+      }
+      total_steps += check;
+      rc = energy(e);
+      if (rc) break;
+      const bool still = std::fabs(e - e_prev) <= tol * std::max(1.0, std::fabs(e));
+      e_prev = e;
+      quiet = still ? quiet + 1 : 0;
+      if (quiet >= 2) break;
+    }
+    ocmps_stepper_destroy(st);
+  }
+  ocmps_store_destroy(tmp);
+  if (rc) return rc;
+  if (energy_out) *energy_out = e_prev;
+  if (steps_out) *steps_out = total_steps;
+  return OCMPS_OK;
 }
 
 // Entanglement entropy of every bond of the slices first .. first+count-1 (include/correlations.hpp:119-148:
