@@ -45,6 +45,29 @@ class Args {
   void add(const std::string& k, double v) { vals_[key(k)] = v; }
 };
 
+// ---- InputGroup(file, "input"): the `name = value` blocks the reference's main programs read (main/OptimizeRamp.cpp:27-50) ----
+//   input
+//   {
+//       N = 5
+//       useBFGS = no
+//   }
+class InputGroup {
+  std::map<std::string, std::string> kv_;
+  std::string file_, group_;
+  const std::string* find(const std::string& k) const { auto it = kv_.find(k); return it == kv_.end() ? nullptr : &it->second; }
+ public:
+  InputGroup(const std::string& filename, const std::string& groupname);
+  bool has(const std::string& k) const { return kv_.count(k) > 0; }
+  double getReal(const std::string& k) const;                      // mandatory: throws std::runtime_error if absent
+  double getReal(const std::string& k, double def) const { return has(k) ? getReal(k) : def; }
+  int getInt(const std::string& k) const;
+  int getInt(const std::string& k, int def) const { return has(k) ? getInt(k) : def; }
+  bool getYesNo(const std::string& k) const;
+  bool getYesNo(const std::string& k, bool def) const { return has(k) ? getYesNo(k) : def; }
+  std::string getString(const std::string& k) const;
+  std::string getString(const std::string& k, const std::string& def) const { return has(k) ? getString(k) : def; }
+};
+
 // ---- SiteSet / BoseHubbard(N, d): N sites with occupations 0..d (include/BH_sites.h:10-58) ----
 class SiteSet {
  protected:

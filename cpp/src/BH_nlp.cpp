@@ -107,6 +107,9 @@ void BH_nlp::finalize_solution(SolverReturn, Ipopt::Index n, const Number* x, co
   } else {
     std::cout << "Unable to open file\n";
   }
+  // The reference computes the final Hessians unconditionally (src/BH_nlp.cpp:258-261), which in BFGS mode reads stores that were
+  // never allocated (README.md:5).  Here the xi / K.xi stores are switched back on first, so the two files are always written.
+  if (optControlProb.useBFGS()) optControlProb.setBFGS(false);
   const auto Hgroup = optControlProb.getHessian(fin);
   optControlProb.setGRAPE(true);
   const auto Hgrape = optControlProb.getHessian(u1);

@@ -95,3 +95,70 @@ void overlap(const IQMPS& a, const IQMPS& b, Real& re, Real& im) {
 }
 
 }  // namespace itensor
+
+// ---- InputGroup ----
+#include <cctype>
+#include <fstream>
+#include <sstream>
+namespace itensor {
+InputGroup::InputGroup(const std::string& filename, const std::string& groupname) : file_(filename), group_(groupname) {
+  std::ifstream f(filename);
+  if (!f.is_open()) throw std::runtime_error("InputGroup: cannot open " + filename);
+  std::stringstream ss;
+  ss << f.rdbuf();
+  std::string txt = ss.str();
+  for (size_t i = 0; i < txt.size(); ++i)                    // strip comments: '#' or '//' to the end of the line
+    if (txt[i] == '#' || (txt[i] == '/' && i + 1 < txt.size() && txt[i + 1] == '/')) { while (i < txt.size() && txt[i] != '\n') txt[i++] = ' '; }
+  size_t pos = 0;
+  bool found = false;
+  while ((pos = txt.find(groupname, pos)) != std::string::npos) {
+    const bool left_ok = pos == 0 || std::isspace((unsigned char)txt[pos - 1]);
+    size_t q = pos + groupname.size();
+    while (q < txt.size() && std::isspace((unsigned char)txt[q])) ++q;
+    if (left_ok && q < txt.size() && txt[q] == '{') { pos = q + 1; found = true; break; }
+    pos += groupname.size();
+  }
+  if (!found) throw std::runtime_error("InputGroup: group '" + groupname + "' not found in " + filename);
+  const size_t end = txt.find('}', pos);
+  if (end == std::string::npos) throw std::runtime_error("InputGroup: missing '}' in " + filename);
+  std::stringstream body(txt.substr(pos, end - pos));
+  std::string line;
+  while (std::getline(body, line)) {
+    const size_t eq = line.find('=');
+    if (eq == std::string::npos) continue;
+    auto trim = [](std::string v) {
+      size_t a = 0, b = v.size();
+      while (a < b && std::isspace((unsigned char)v[a])) ++a;
+      while (b > a && std::isspace((unsigned char)v[b - 1])) --b;
+      return v.substr(a, b - a);
+    };
+    const std::string k = trim(line.substr(0, eq)), v = trim(line.substr(eq + 1));
+    if (!k.empty() && !v.empty()) kv_[k] = v;
+  }
+}
+double InputGroup::getReal(const std::string& k) const {
+  const std::string* v = find(k);
+  if (!v) throw std::runtime_error("InputGroup: mandatory key '" + k + "' missing in group '" + group_ + "' of " + file_);
+  return std::stod(*v);
+}
+int InputGroup::getInt(const std::string& k) const {
+  const std::string* v = find(k);
+  if (!v) throw std::runtime_error("InputGroup: mandatory key '" + k + "' missing in group '" + group_ + "' of " + file_);
+  return (int)std::stol(*v);
+}
+bool InputGroup::getYesNo(const std::string& k) const {
+  const std::string* v = find(k);
+  if (!v) throw std::runtime_error("InputGroup: mandatory key '" + k + "' missing in group '" + group_ + "' of " + file_);
+  std::string t = *v;
+  for (char& c : t) c = (char)std::tolower((unsigned char)c);
+  if (t == "yes" || t == "y" || t == "true" || t == "1") return true;
+  if (t == "no" || t == "n" || t == "false" || t == "0") return false;
+  throw std::runtime_error("InputGroup: key '" + k + "' is neither yes nor no");
+}
+std::string InputGroup::getString(const std::string& k) const {
+  const std::string* v = find(k);
+  if (!v) throw std::runtime_error("InputGroup: mandatory key '" + k + "' missing");
+  return *v;
+}
+}  // namespace itensor
+
