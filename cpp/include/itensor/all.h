@@ -96,8 +96,10 @@ class IQMPS {
   IQMPS() {}
   IQMPS(int L, int D, int chi_cap);                       // empty device MPS
   // host data: bond_dims[L+1], charges (concatenated over bonds), tensors (concatenated, row-major [l][s][r])
+  // llim / rlim: ITensor's orthogonality limits of the data (sites <= llim left-orthonormal, sites >= rlim right-orthonormal);
+  // anything but (0, 2) is gauged to site 1 on the device after the upload (llim = 0, rlim = L+1: nothing assumed)
   IQMPS(int L, int D, int chi_cap, const std::vector<int>& bond_dims, const std::vector<int>& charges,
-        const std::vector<Cplx>& tensors);
+        const std::vector<Cplx>& tensors, int llim = 0, int rlim = 2);
   IQMPS(const IQMPS& o);                                  // deep copy on the device (ITensor copies are values)
   IQMPS& operator=(const IQMPS& o);
   IQMPS(IQMPS&&) = default;
@@ -108,7 +110,7 @@ class IQMPS {
   int capacity() const { return cap_; }
   ocmps_mps* handle() const { return p_ ? p_->h : nullptr; }
   std::vector<int> bondDims() const;
-  void toHost(std::vector<int>& bond_dims, std::vector<int>& charges, std::vector<Cplx>& tensors) const;
+  void toHost(std::vector<int>& bond_dims, std::vector<int>& charges, std::vector<Cplx>& tensors, int* llim = nullptr, int* rlim = nullptr) const;
   IQMPS withCapacity(int chi_cap) const;                  // re-homes the state in buffers of another capacity
 };
 inline LinkDim linkInd(const IQMPS& psi, int b) { return LinkDim{(long)psi.bondDims().at(b)}; }   // main/AnalyzeBondDim.cpp:140

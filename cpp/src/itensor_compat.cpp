@@ -21,10 +21,11 @@ IQMPS::IQMPS(int L, int D, int chi_cap) : p_(std::make_shared<Holder>()), L_(L),
 }
 
 IQMPS::IQMPS(int L, int D, int chi_cap, const std::vector<int>& bond_dims, const std::vector<int>& charges,
-             const std::vector<Cplx>& tensors)
+             const std::vector<Cplx>& tensors, int llim, int rlim)
     : IQMPS(L, D, chi_cap) {
-  ocmps_check(ocmps_mps_upload(p_->h, bond_dims.data(), charges.data(), reinterpret_cast<const double*>(tensors.data()), 0, 2),
+  ocmps_check(ocmps_mps_upload(p_->h, bond_dims.data(), charges.data(), reinterpret_cast<const double*>(tensors.data()), llim, rlim),
               "ocmps_mps_upload");
+  if (llim != 0 || rlim != 2) ocmps_check(ocmps_mps_position1(p_->h), "ocmps_mps_position1");
 }
 
 IQMPS::IQMPS(const IQMPS& o) : L_(o.L_), D_(o.D_), cap_(o.cap_) {
@@ -50,7 +51,7 @@ std::vector<int> IQMPS::bondDims() const {
   return d;
 }
 
-void IQMPS::toHost(std::vector<int>& bond_dims, std::vector<int>& charges, std::vector<Cplx>& tensors) const {
+void IQMPS::toHost(std::vector<int>& bond_dims, std::vector<int>& charges, std::vector<Cplx>& tensors, int* llim, int* rlim) const {
   long long ne = 0, nq = 0;
   ocmps_check(ocmps_mps_sizes(p_->h, &ne, &nq), "ocmps_mps_sizes");
   bond_dims.assign(L_ + 1, 0);
@@ -59,14 +60,17 @@ void IQMPS::toHost(std::vector<int>& bond_dims, std::vector<int>& charges, std::
   int ll = 0, rl = 0;
   ocmps_check(ocmps_mps_download(p_->h, bond_dims.data(), charges.data(), reinterpret_cast<double*>(tensors.data()), &ll, &rl),
               "ocmps_mps_download");
+  if (llim) *llim = ll;
+  if (rlim) *rlim = rl;
 }
 
 IQMPS IQMPS::withCapacity(int chi_cap) const {
   if (chi_cap == cap_) return *this;
   std::vector<int> d, q;
   std::vector<Cplx> t;
-  toHost(d, q, t);
-  return IQMPS(L_, D_, chi_cap, d, q, t);
+  int ll = 0, rl = 2;
+  toHost(d, q, t, &ll, &rl);
+  return IQMPS(L_, D_, chi_cap, d, q, t, ll, rl);
 }
 
 Real norm(const IQMPS& psi) {

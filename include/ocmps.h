@@ -67,6 +67,9 @@ int ocmps_mps_sizes(ocmps_mps* mps, long long* n_elems, long long* n_charges);
 int ocmps_mps_download(ocmps_mps* mps, int* bond_dims, int* charges, double* tensors, int* llim, int* rlim);
 int ocmps_mps_bond_dims(ocmps_mps* mps, int* bond_dims);       /* linkInd(psi,b).m(), main/AnalyzeBondDim.cpp:140 */
 int ocmps_mps_copy(ocmps_mps* dst, ocmps_mps* src);            /* IQMPS copy, e.g. src/OptimalControl.cpp:379-380 */
+/* psi.position(1): moves the orthogonality centre to site 1 with the engine's gauge moves, starting from the limits given at
+ * upload (llim = 0, rlim = L+1: no site assumed orthogonal).  step / sweeps / apply_K require the centre at site 1. */
+int ocmps_mps_position1(ocmps_mps* mps);
 int ocmps_mps_norm(ocmps_mps* mps, double* out);               /* itensor::norm(psi), src/OptimalControl.cpp:257 */
 /* overlapC(a,b) = <a|b> (first argument conjugated), src/OptimalControl.cpp:242,261,272,450 */
 int ocmps_overlap(ocmps_mps* a, ocmps_mps* b, double* re_im);

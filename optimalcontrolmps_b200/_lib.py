@@ -16,7 +16,7 @@ SYMBOLS = [
     "ocmps_last_error", "ocmps_version", "ocmps_launch_count", "ocmps_profile_enable", "ocmps_profile_read",
     "ocmps_ctx_create", "ocmps_ctx_destroy", "ocmps_ctx_synchronize", "ocmps_ctx_trim", "ocmps_timer_start", "ocmps_timer_stop",
     "ocmps_mps_create", "ocmps_mps_destroy", "ocmps_mps_upload", "ocmps_mps_sizes", "ocmps_mps_download",
-    "ocmps_mps_bond_dims", "ocmps_mps_copy", "ocmps_mps_norm", "ocmps_overlap", "ocmps_overlap_K",
+    "ocmps_mps_bond_dims", "ocmps_mps_copy", "ocmps_mps_position1", "ocmps_mps_norm", "ocmps_overlap", "ocmps_overlap_K",
     "ocmps_stepper_create", "ocmps_stepper_destroy", "ocmps_stepper_set_tstep", "ocmps_stepper_get_tstep",
     "ocmps_step", "ocmps_apply_K", "ocmps_ground_state", "ocmps_stepper_schedule", "ocmps_stepper_gate",
     "ocmps_store_create", "ocmps_store_destroy", "ocmps_store_get", "ocmps_store_put", "ocmps_store_bond_dims",
@@ -61,6 +61,7 @@ def load():
         "ocmps_mps_upload": (i, [vp, pi, pi, pd, i, i]),
         "ocmps_mps_sizes": (i, [vp, pll, pll]),
         "ocmps_mps_download": (i, [vp, pi, pi, pd, pi, pi]),
+        "ocmps_mps_position1": (i, [vp]),
         "ocmps_mps_bond_dims": (i, [vp, pi]),
         "ocmps_mps_copy": (i, [vp, vp]),
         "ocmps_mps_norm": (i, [vp, pd]),

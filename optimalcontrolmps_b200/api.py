@@ -171,6 +171,11 @@ class DeviceMPS:
             qoff += int(dims[b])
         return IQMPS(A, q, ll.value, rl.value)
 
+    def position1(self):
+        """``psi.position(1)``: gauge moves of the engine from the orthogonality limits of the uploaded state to site 1."""
+        _lib.check(self.ctx.lib.ocmps_mps_position1(self.h))
+        return self
+
     def copy_from(self, other: "DeviceMPS"):
         _lib.check(self.ctx.lib.ocmps_mps_copy(self.h, other.h))
         return self
@@ -408,7 +413,12 @@ class BH_tDMRG:
 
     # -- helpers
     def to_device(self, psi: IQMPS) -> DeviceMPS:
-        return DeviceMPS(self.ctx, self.L, self.D, self.chi_cap).upload(psi)
+        """Uploads a host state; if its orthogonality limits say the centre is not at site 1 it is gauged there with the
+        engine's own moves (the reference's step starts with psi.position(), src/BH_tDMRG.cpp:139-148)."""
+        dev = DeviceMPS(self.ctx, self.L, self.D, self.chi_cap).upload(psi)
+        if (psi.llim, psi.rlim) != (0, 2):
+            dev.position1()
+        return dev
 
     def new_mps(self) -> DeviceMPS:
         return DeviceMPS(self.ctx, self.L, self.D, self.chi_cap)

@@ -1169,6 +1169,45 @@ int ocmps_mps_copy(ocmps_mps* dst, ocmps_mps* src) {
   return OCMPS_OK;
 }
 
+// psi.position(1) (ITensor MPS::position via orthMPS) from the orthogonality limits the state was uploaded with:
+// block-SVD gauge moves from site rlim-1 down to site 2 (Cutoff 1e-16, Maxm 5000: numerical-rank drops only), S.V pushed to the
+// left.  Every other entry point that needs a gauge (step, sweeps, K|psi>) requires the centre at site 1 and says so; this is
+// the call that establishes it for a state in any other gauge (llim = 0, rlim = L+1: nothing is assumed orthogonal).
+int ocmps_mps_position1(ocmps_mps* m) {
+  if (!m) return fail(OCMPS_ERR_INVALID, "null argument");
+  const Layout& lay = m->lay;
+  const int L = lay.L, D = lay.D;
+  if (m->llim != 0) {
+    // sites left of the centre are left-orthonormal by assumption; moving the centre to site 1 re-gauges them all
+    if (m->llim < 0 || m->llim > L - 1) return fail(OCMPS_ERR_INVALID, "position: bad orthogonality limits");
+  }
+  int rlim = std::min(std::max(m->rlim, m->llim + 2), L + 1);
+  if (rlim <= 2) { m->llim = 0; m->rlim = 2; return OCMPS_OK; }
+  CK(cudaSetDevice(m->ctx->dev));
+  WsLease lease;
+  int rc = lease.acquire(m->ctx, L, D, lay.cap, 1);
+  if (rc) return rc;
+  Workspace* ws = lease[0];
+  cudaStream_t s = ws->stream;
+  TruncParams tpo{MIN_CUT, MAX_M, 1, 0, 0, 0};
+  for (int b = rlim - 2; b >= 1; --b) {          // bond b joins sites b and b+1 (1-based): SVD of site b+1, U.S pushed into site b
+    const int j = b, jn = b - 1;
+    DecompArgs a;
+    a.D = D; a.kind = DK_ORTH_RIGHT;
+    a.dimNew = m->dim(b); a.qNew = m->q(b); a.partner = ws->cbuf;
+    a.dimL = m->dim(b); a.dimR = m->dim(b + 1); a.qL = m->q(b); a.qR = m->q(b + 1);
+    a.X = m->site(j); a.iso = m->other(j);
+    a.nb_in = m->site(jn); a.nb_out = m->other(jn); a.dimNb = m->dim(b - 1);
+    a.qNb = fused_push_enabled() ? m->q(b - 1) : nullptr;
+    tpo.cap = lay.capb[b];
+    run_decomp(ws, a, tpo, lay.capb[b], lay.capb[b + 1], lay.capb[b], s);
+    if (!a.qNb) { launch_zgemm(ws->db.descs + 1, 1, lay.capb[b - 1] * D, lay.capb[b], s); g_ocmps_launches += 1; }
+    m->cur[j] ^= 1; m->cur[jn] ^= 1;
+  }
+  m->llim = 0; m->rlim = 2;
+  return lease.finish();
+}
+
 int ocmps_mps_norm(ocmps_mps* m, double* out) {
   if (!m || !out) return fail(OCMPS_ERR_INVALID, "null argument");
   if (m->llim + 2 != m->rlim) return fail(OCMPS_ERR_INVALID, "norm: MPS has no single orthogonality centre");

@@ -142,3 +142,37 @@ def test_trim_releases_idle_workspaces_and_everything_still_works():
     assert np.array_equal(H0, H1)
     assert p.getCost(u, True) == c0
     assert np.max(np.abs(H0 - z["hessian"])) / np.max(np.abs(z["hessian"])) < 1e-6
+
+
+def test_state_in_another_gauge_is_moved_to_site_1():
+    """A host state whose orthogonality limits are not (0, 2) -- here: nothing assumed orthogonal, and centre at the last site -- is
+    gauged to site 1 with the engine's own moves on upload (psi.position(), src/BH_tDMRG.cpp:139-148) and then evolves like the
+    oracle's copy of it."""
+    import optimalcontrolmps_b200 as oc
+    from conftest import random_symmetric_mps
+    from oracle import bh_mps as ob
+    L, d, chi = 6, 4, 16
+    D = d + 1
+    st = oc.BH_tDMRG(oc.BoseHubbard(L, d), 1.0, 0.01, oc.Args("Cutoff=", 1e-10, "Maxm=", chi), chi_cap=chi)
+    so = ob.BHStepper(L, D, 1.0, 0.01, ob.TruncArgs(cutoff=1e-10, maxm=chi))
+    base = random_symmetric_mps(L, D, 6, chi, seed=5)
+    for case in ("none", "right_end"):
+        psi = base.copy()
+        if case == "none":                              # destroy the canonical form: rescale and mix nothing -> claim no orthogonality
+            psi.A[2] = psi.A[2] * 1.7
+            psi.llim, psi.rlim = 0, L + 1
+        else:
+            psi.position(L)                             # centre at the last site
+        want = psi.copy()
+        want.position(1)
+        dev = st.to_device(to_host(psi))
+        got = to_oracle(dev.download())
+        assert (got.llim, got.rlim) == (0, 2)
+        assert abs(ob.overlap(want, got) - ob.overlap(want, want)) < 1e-11 * abs(ob.overlap(want, want))
+        assert abs(dev.norm() - want.norm()) < 1e-11 * want.norm()
+        for k in range(2):
+            st.step(dev, 3.0, 3.5, True)
+            so.step(want, 3.0, 3.5, True)
+        got = to_oracle(dev.download())
+        assert got.bond_dims() == want.bond_dims()
+        assert abs(abs(ob.overlap(want, got)) - 1.0) < 1e-10
