@@ -40,6 +40,14 @@ constexpr int JAC_BLOCKED_ROWS = 64;      // 4 rows per warp, JAC_THREADS / 32 w
 constexpr double JAC_TOL2 = 1e-28;        // rotate while |<p|q>|^2 > tol^2 <p|p><q|q>, tol = 1e-14
 constexpr double DEFLATE_REL = 1e-30;     // vectors below this fraction of the block's weight are numerically zero
 constexpr int NV_MAX = 2048;              // max number of vectors in one decomposition
+// cluster kernel for large blocks (jacobi_big_kernel)
+constexpr int BJ_C = 8;                   // CTAs per cluster
+constexpr int BJ_TPP = 4;                 // lanes per pair
+constexpr int BJ_MAX_ROWS = 256;          // rows of R
+constexpr int BJ_SLOTS = BJ_MAX_ROWS / 2; // pair slots
+constexpr int BJ_THREADS = BJ_SLOTS * BJ_TPP;      // 512
+constexpr int BJ_MAX_EPL = 8;             // columns per lane: slices of up to 32 columns, rows of R up to 256 long
+constexpr int BJ_MIN_CAP = 112;           // launched when the capacities allow blocks with at least this many rows
 
 // ------------------------------------------------------------------------------------------------
 // setup: charges of rows / columns, block table, sorted index lists
@@ -492,7 +500,7 @@ __device__ __forceinline__ int qr_pivoted_cached(QrState& q) {
 // pair's elements stay in registers between the dot product and the rotation.  A block is handled by exactly one
 // instantiation; splitting them keeps the hot loop of the common case small enough for the instruction caches.
 template <bool SMEM, bool CACHED>
-__global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a, DecompBuffers b, int smem_elems, double rank_tol) {
+__global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a, DecompBuffers b, int smem_elems, double rank_tol, int big_on) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_rot, s_keff, s_big;
   __shared__ unsigned long long s_key[3];       // pivot keys of the QR steps j, j+1 and the one being reset (generic path)
@@ -512,6 +520,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   const int ldpad = ((nv + 15) >> 4) << 4;
   const bool can_cache = nv <= 16 * JAC_EPL && (nv < len ? nv : len) * ldpad <= smem_elems;
   if (fits != SMEM || (SMEM && can_cache != CACHED)) return;   // another instantiation handles this block
+  if (big_on && !(SMEM && CACHED) && nv <= BJ_MAX_ROWS && len <= BJ_MAX_ROWS) return;   // taken by qr_big_kernel (cluster)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = JAC_THREADS / 32;
   const int half = lane >> 4, hl = lane & 15;
   cplx* Ya = b.ywork + B.ws_off;                       // region A: final Z (k x nv, physical vector order)
@@ -691,8 +700,19 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
     // rows; a kernel of its own so that its register allocation is not shared with the QR phase)
     double* hF = b.scratch_d + 7 * NV_MAX;
     int* hK = reinterpret_cast<int*>(b.scratch_d + 7 * NV_MAX + OCMPS_MAX_BLK);
-    const bool handover = CACHED && keff <= JAC_BLOCKED_ROWS;
-    if (tid == 0) { hF[blockIdx.x] = F; hK[blockIdx.x] = handover ? keff : -1; }
+    // blocks with more rows (or longer rows) than that go to the cluster kernel jacobi_big_kernel when it is launched
+    // (big_on): R distributed by columns over a thread-block cluster, up to 256 rows of up to 256 columns
+    int* hB = hK + OCMPS_MAX_BLK;
+    int* hS = hB + OCMPS_MAX_BLK;
+    const bool handover_small = CACHED && keff <= JAC_BLOCKED_ROWS;
+    const bool handover_big = !handover_small && big_on && keff <= BJ_MAX_ROWS && nv <= BJ_MAX_ROWS;
+    const bool handover = handover_small || handover_big;
+    if (tid == 0) {
+      hF[blockIdx.x] = F;
+      hK[blockIdx.x] = handover_small ? keff : -1;
+      hB[blockIdx.x] = handover_big ? keff : -1;
+      hS[blockIdx.x] = ldz;
+    }
     if (handover) {
       short* gperm = reinterpret_cast<short*>(b.scratch_d + 4 * NV_MAX) + B.p_off;
       for (int i = tid; i < nv; i += JAC_THREADS) gperm[i] = perm[i];
@@ -951,6 +971,580 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_rot_kernel(DecompArgs a, D
     } else if (lane == 0) {
       b.P[B.p_off + v] = 0.0;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Large blocks: one-sided Jacobi on the rows of R distributed over a thread-block cluster
+// ------------------------------------------------------------------------------------------------
+// A block with more than 64 rows of R (chi_cap >= ~110: K|psi> with its 2 chi bonds, the chi = 150 / 256 configurations) does not
+// fit the register-resident kernel, and from 200 KB on not even one SM's shared memory: the generic loops then stream every
+// pair of rows through L2 in every round (measured: 11 ms per decomposition at chi = 256).  Here the COLUMNS of R are split over
+// the BJ_C = 8 CTAs of a cluster: every CTA keeps all rows (up to 256) of its slice (up to 32 columns, 128 KB) in shared memory.
+// A round: partial dot products of the slice (4 lanes per pair, <= 8 columns per lane) -> one exchange of the 16-byte partials
+// through distributed shared memory (st.async carries data + mbarrier complete_tx in one message; double buffered) -> every CTA
+// sums the partials in rank order, so all CTAs compute bitwise identical angles, norms and convergence flags and never have
+// to agree on anything else -> rotation of the slice.  Exact squared norms at the start of a sweep go through the same exchange.
+// For blocks that FIT one SM this layout is no faster than jacobi_rot_kernel (profiles/r02_cluster_jacobi.md); it is the
+// path for the blocks that do not.
+namespace clus {
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa(unsigned addr, unsigned rank) {
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_v2(unsigned raddr, double a, double b, unsigned rmbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(raddr), "d"(a), "d"(b), "r"(rmbar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void cluster_sync() { asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+}  // namespace clus
+
+// ------------------------------------------------------------------------------------------------
+// Large blocks, first half: Householder QR with column pivoting, the VECTORS distributed over the cluster
+// ------------------------------------------------------------------------------------------------
+// CTA r of the 8 owns the vectors [r wv, (r+1) wv), wv = ceil(nv / 8) <= 32, each up to 256 components long, in shared memory
+// (<= 128 KB), one half-warp per vector.  A step: (1) every CTA's best pivot candidate -- (norm bits | position) keys as in the
+// single-CTA kernel -- is exchanged through distributed shared memory, so all CTAs pick the same pivot; (2) the pivot vector is
+// pulled from its owner's shared memory (ld.shared::cluster) into every CTA; (3) every CTA forms the reflector from the exact
+// pivot norm (bitwise the same everywhere), applies it to the vectors it owns and downdates their norms with the xGEQP3
+// safeguard.  Position bookkeeping, R's diagonal and the rank test are replicated, so nothing else has to be agreed on.
+// At the end every CTA writes the columns of R that belong to its vectors; jacobi_big_kernel takes over.
+struct QbShared {
+  unsigned long long key[2][BJ_C][2];     // exchanged candidates (double buffered), [buffer][source rank][key, unused]
+  unsigned long long mbar[2];
+  unsigned long long best;                // local candidate of the step (atomicMax)
+  double red[BJ_THREADS / 32];
+  double ncur[32], nref[32];              // trailing norms of the owned vectors (downdated / last exact value)
+  double rdr[BJ_MAX_ROWS], rdi[BJ_MAX_ROWS];
+  short pos2phys[BJ_MAX_ROWS], posof[BJ_MAX_ROWS];
+  double F;
+};
+
+__device__ __forceinline__ void st_async_b64x2(unsigned raddr, unsigned long long a, unsigned long long b, unsigned rmbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(raddr), "l"(a), "l"(b), "r"(rmbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned mbar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAITC_%=:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONEC_%=;\nbra WAITC_%=;\nDONEC_%=:\n}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+// every CTA contributes one 64-bit value; afterwards out[r] holds the value of rank r in every CTA.  Called by all threads after
+// a __syncthreads() that ordered the CTA's shared-memory writes of the step (they are released to the cluster here).
+__device__ __forceinline__ void qb_allgather(QbShared& sh, unsigned& xcount, unsigned rank, unsigned long long mine, unsigned long long (&out)[BJ_C]) {
+  const unsigned b = xcount & 1u, par = (xcount >> 1) & 1u;
+  ++xcount;
+  const unsigned mb = clus::smem_u32(&sh.mbar[b]);
+  if (threadIdx.x == 0) {
+    sh.key[b][rank][0] = mine;
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");       // the vectors updated in this step are visible to remote loads
+    const unsigned la = clus::smem_u32(&sh.key[b][rank][0]);
+#pragma unroll
+    for (unsigned p = 1; p < (unsigned)BJ_C; ++p) {
+      const unsigned peer = (rank + p) % BJ_C;
+      st_async_b64x2(clus::mapa(la, peer), mine, 0ull, clus::mapa(mb, peer));
+    }
+  }
+  mbar_wait_cluster(mb, par);
+  if (threadIdx.x == 0) clus::mbar_expect(mb, (unsigned)((BJ_C - 1) * 16));
+  __syncthreads();                                               // (own value written by thread 0)
+#pragma unroll
+  for (int r = 0; r < BJ_C; ++r) out[r] = sh.key[b][r][0];
+}
+
+__global__ void __launch_bounds__(BJ_THREADS) qr_big_kernel(DecompArgs a, DecompBuffers b, int smem_elems, double rank_tol) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ QbShared sh;
+  constexpr unsigned long long KEY_POS = 2047ull;
+  const DecompWork* w = b.dw;
+  const int blk = blockIdx.x / BJ_C;
+  if (blk >= w->nblocks) return;
+  const DecompBlock B = w->blk[blk];
+  const int nv = B.nv, len = B.len, ld = w->ld, mode = w->mode;
+  {   // the same routing test as jacobi_blocks_kernel: only the blocks its register-cached instantiation does not take
+    const bool fits = nv * len <= smem_elems && nv <= JAC_NV_SMEM;
+    const int ldpad = ((nv + 15) >> 4) << 4;
+    const bool can_cache = nv <= 16 * JAC_EPL && (nv < len ? nv : len) * ldpad <= smem_elems;
+    if ((fits && can_cache) || nv > BJ_MAX_ROWS || len > BJ_MAX_ROWS) return;
+  }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, half = lane >> 4, hl = lane & 15;
+  const unsigned rank = clus::cluster_rank();
+  const int wv = (nv + BJ_C - 1) / BJ_C;                     // vectors per CTA
+  const int v0 = (int)rank * wv;
+  const int nown = max(0, min(nv, v0 + wv) - v0);
+  cplx* Yv = reinterpret_cast<cplx*>(smem_raw);              // [owned vector][component], row stride len
+  cplx* xp = Yv + (size_t)32 * BJ_MAX_ROWS;                  // pivot vector of the step
+  const int* vidx = b.vec_idx + B.vec_off;
+  const int* cidx = b.comp_idx + B.comp_off;
+  cplx* Yb = b.ywork + b.ywork_half + B.ws_off;
+  unsigned xcount = 0;
+  if (tid == 0) {
+    clus::mbar_init(clus::smem_u32(&sh.mbar[0]), 1);
+    clus::mbar_init(clus::smem_u32(&sh.mbar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    clus::mbar_expect(clus::smem_u32(&sh.mbar[0]), (unsigned)((BJ_C - 1) * 16));
+    clus::mbar_expect(clus::smem_u32(&sh.mbar[1]), (unsigned)((BJ_C - 1) * 16));
+  }
+  // gather the owned vectors
+  if (mode == 0) {
+    for (int e = tid; e < nown * len; e += BJ_THREADS) {
+      const int c = e / nown, vl = e % nown;
+      Yv[vl * len + c] = a.X[(size_t)cidx[c] * ld + vidx[v0 + vl]];
+    }
+  } else {
+    for (int e = tid; e < nown * len; e += BJ_THREADS) {
+      const int vl = e / len, c = e % len;
+      Yv[vl * len + c] = a.X[(size_t)vidx[v0 + vl] * ld + cidx[c]];
+    }
+  }
+  for (int i = tid; i < nv; i += BJ_THREADS) { sh.pos2phys[i] = (short)i; sh.posof[i] = (short)i; }
+  __syncthreads();
+  const int hv = 2 * warp + half;                            // the owned vector of this half-warp
+  {
+    double sq = 0.0;
+    if (hv < nown) for (int c = hl; c < len; c += 16) { const cplx u = Yv[hv * len + c]; sq += u.x * u.x + u.y * u.y; }
+    sq = half_sum(sq);
+    if (hv < nown && hl == 0) { sh.ncur[hv] = sq; sh.nref[hv] = sq; }
+  }
+  __syncthreads();
+  clus::cluster_sync();
+  {   // block weight F: sum of all initial norms, rank order
+    double part = 0.0;
+    for (int i = 0; i < nown; ++i) part += sh.ncur[i];
+    unsigned long long all[BJ_C];
+    qb_allgather(sh, xcount, rank, (unsigned long long)__double_as_longlong(part), all);
+    double F = 0.0;
+#pragma unroll
+    for (int r = 0; r < BJ_C; ++r) F += __longlong_as_double((long long)all[r]);
+    if (tid == 0) sh.F = F;
+    __syncthreads();
+  }
+  const double F = sh.F;
+  const double rtol_abs = F * rank_tol;
+  const int kmax = nv < len ? nv : len;
+  int keff = 0;
+  const long long t_qr0 = clock64();
+#ifdef OCMPS_JAC_TRACE
+  long long tp[4] = {0, 0, 0, 0};
+  long long tl = clock64();
+#define QB_MARK(i) { const long long tn = clock64(); tp[i] += tn - tl; tl = tn; }
+#else
+#define QB_MARK(i)
+#endif
+  for (int j = 0; j < kmax; ++j) {
+    // (1) pivot: local candidate among the owned vectors that are still in play, then the cluster-wide maximum
+    if (tid == 0) sh.best = 0ull;
+    __syncthreads();
+    if (hv < nown && hl == 0) {
+      const int pos = sh.posof[v0 + hv];
+      if (pos >= j) atomicMax(&sh.best, ((unsigned long long)__double_as_longlong(sh.ncur[hv]) & ~KEY_POS) | (KEY_POS - (unsigned long long)pos));
+    }
+    __syncthreads();
+    unsigned long long all[BJ_C];
+    qb_allgather(sh, xcount, rank, sh.best, all);
+    unsigned long long gbest = 0ull;
+#pragma unroll
+    for (int r = 0; r < BJ_C; ++r) gbest = all[r] > gbest ? all[r] : gbest;
+    const int bpos = (int)(KEY_POS - (gbest & KEY_POS));
+    const int pv = sh.pos2phys[bpos], pj = sh.pos2phys[j];
+    QB_MARK(0)
+    // (2) pull the pivot vector (components j .. len-1) from its owner
+    {
+      const unsigned owner = (unsigned)(pv / wv);
+      const cplx* src = Yv + (size_t)(pv - (int)owner * wv) * len;
+      if (owner == rank) {
+        for (int c = j + tid; c < len; c += BJ_THREADS) xp[c] = src[c];
+      } else {
+        const unsigned base = clus::mapa(clus::smem_u32(src), owner);
+        for (int c = j + tid; c < len; c += BJ_THREADS) {
+          double xr, xi;
+          asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(xr), "=d"(xi) : "r"(base + (unsigned)c * 16u) : "memory");
+          xp[c] = make_double2(xr, xi);
+        }
+      }
+    }
+    __syncthreads();
+    QB_MARK(1)
+    // (3) exact norm of the pivot vector, the same bits in every CTA (fixed reduction order)
+    {
+      double sq = 0.0;
+      for (int c = j + tid; c < len; c += BJ_THREADS) { const cplx u = xp[c]; sq += u.x * u.x + u.y * u.y; }
+      sq = warp_sum(sq);
+      if (lane == 0) sh.red[warp] = sq;
+    }
+    __syncthreads();
+    double best = 0.0;
+#pragma unroll
+    for (int i = 0; i < BJ_THREADS / 32; ++i) best += sh.red[i];
+    if (!(best > rtol_abs)) break;                              // numerical rank reached (uniform over the cluster)
+    keff = j + 1;
+    const cplx alpha = xp[j];
+    const double inx = rsqrt(best), normx = best * inx;
+    const double a2 = alpha.x * alpha.x + alpha.y * alpha.y;
+    const double ia = a2 > 0.0 ? rsqrt(a2) : 0.0, aabs = a2 * ia;
+    const double phr = a2 > 0.0 ? alpha.x * ia : 1.0, phi = a2 > 0.0 ? alpha.y * ia : 0.0;
+    const double v0r = alpha.x + phr * normx, v0i = alpha.y + phi * normx;
+    const double rb = rsqrt(normx * (normx + aabs));
+    const double beta = rb * rb;
+    if (tid == 0) {
+      sh.rdr[j] = -phr * normx; sh.rdi[j] = -phi * normx;       // R_jj
+      sh.pos2phys[bpos] = (short)pj; sh.pos2phys[j] = (short)pv;
+      sh.posof[pj] = (short)bpos; sh.posof[pv] = (short)j;
+    }
+    __syncthreads();
+    QB_MARK(2)
+    // (4) reflector on the owned vectors that are still in play (all 32 lanes take part in the shuffles; `act` is per half-warp)
+    {
+      const int pos = hv < nown ? (int)sh.posof[v0 + hv] : -1;
+      const bool act = pos > j;
+      cplx* y = Yv + (size_t)(act ? hv : 0) * len;
+      double wr = 0.0, wi = 0.0;
+      if (act) {
+        for (int c = j + hl; c < len; c += 16) {
+          cplx vv = xp[c];
+          if (c == j) { vv.x = v0r; vv.y = v0i; }
+          const cplx yy = y[c];
+          wr += vv.x * yy.x + vv.y * yy.y;      // conj(v) * y
+          wi += vv.x * yy.y - vv.y * yy.x;
+        }
+      }
+      wr = half_sum(wr); wi = half_sum(wi);
+      double rji2 = 0.0;
+      if (act) {
+        const double fr = beta * wr, fi = beta * wi;
+        for (int c = j + hl; c < len; c += 16) {
+          cplx vv = xp[c];
+          if (c == j) { vv.x = v0r; vv.y = v0i; }
+          cplx yy = y[c];
+          yy.x -= fr * vv.x - fi * vv.y;
+          yy.y -= fr * vv.y + fi * vv.x;
+          y[c] = yy;
+          if (c == j) rji2 = yy.x * yy.x + yy.y * yy.y;
+        }
+      }
+      rji2 = __shfl_sync(0xffffffffu, rji2, lane & 16);          // component j is owned by lane 0 of the half-warp
+      double tnew = 0.0;
+      bool redo = false;
+      if (act) {
+        tnew = sh.ncur[hv] - rji2;
+        redo = !(tnew > 1.5e-8 * sh.nref[hv]);
+      }
+      if (__any_sync(0xffffffffu, redo)) {                        // rare: exact trailing norm (xGEQP3 safeguard)
+        double tail = 0.0;
+        if (act && redo) for (int c = j + 1 + hl; c < len; c += 16) { const cplx yy = y[c]; tail += yy.x * yy.x + yy.y * yy.y; }
+        tail = half_sum(tail);
+        if (act && redo) { tnew = tail; if (hl == 0) sh.nref[hv] = tail; }
+      }
+      if (act && hl == 0) sh.ncur[hv] = tnew > 0.0 ? tnew : 0.0;
+    }
+    __syncthreads();
+    QB_MARK(3)
+  }
+#ifdef OCMPS_JAC_TRACE
+  if (tid == 0 && rank == 0 && nv >= 24)
+    printf("JTQ kind %d blk %d nv %d len %d keff %d qr %lld : exchange %lld pull %lld norm+scalars %lld update %lld\n", a.kind, blk, nv, len, keff,
+           (long long)(clock64() - t_qr0), tp[0], tp[1], tp[2], tp[3]);
+#endif
+  // R (keff x nv, position order, row stride nv) -> global scratch; every CTA writes the columns of its vectors
+  const int ldz = nv;
+  for (int vl = warp; vl < nown; vl += BJ_THREADS / 32) {
+    const int i = sh.posof[v0 + vl];
+    const cplx* y = Yv + (size_t)vl * len;
+    for (int c = lane; c < keff; c += 32) {
+      cplx v = make_double2(0.0, 0.0);
+      if (c < i) v = y[c];
+      else if (c == i) v = make_double2(sh.rdr[c], sh.rdi[c]);
+      Yb[(size_t)c * ldz + i] = v;
+    }
+  }
+  if (rank == 0) {
+    short* gperm = reinterpret_cast<short*>(b.scratch_d + 4 * NV_MAX) + B.p_off;
+    for (int i = tid; i < nv; i += BJ_THREADS) gperm[i] = sh.pos2phys[i];
+    if (tid == 0) {
+      double* hF = b.scratch_d + 7 * NV_MAX;
+      int* hK = reinterpret_cast<int*>(b.scratch_d + 7 * NV_MAX + OCMPS_MAX_BLK);
+      hF[blk] = F;
+      hK[blk] = -1;
+      if (nv >= 64) { const long long t_now = clock64(); atomicAdd(&g_jac_dbg[5], (unsigned long long)(t_now - t_qr0)); atomicAdd(&g_jac_dbg[7], (unsigned long long)(t_now - t_qr0)); }
+      hK[OCMPS_MAX_BLK + blk] = keff;
+      hK[2 * OCMPS_MAX_BLK + blk] = ldz;
+      const double nn = (double)len, mmv = (double)nv;
+      atomicAdd(&g_jac_flops[0], 8.0 * nn * nn * mmv + (56.0 / 3.0) * nn * nn * nn);
+      if (blk == 0) {
+        const double dn = mode == 0 ? (double)w->n : (double)w->m, dm = mode == 0 ? (double)w->m : (double)w->n;
+        atomicAdd(&g_jac_flops[1], 8.0 * dn * dn * dm + (56.0 / 3.0) * dn * dn * dn);
+      }
+    }
+  }
+  clus::cluster_sync();                                   // no CTA may exit while a peer can still read its vectors
+}
+
+struct BjShared {
+  double2 xbuf[2][BJ_C][BJ_SLOTS];        // partials of the exchange in flight (double buffered), [buffer][source rank][slot]
+  unsigned long long mbar[2];
+  double nrm[BJ_MAX_ROWS];
+  int rot, big;
+};
+
+// all-CTAs sum of one (x, y) pair per active slot; every lane of a slot gets the sum (lanes other than the first pass anything).
+// Called by ALL threads; nslots (the same in every CTA) is the number of slots that take part.
+__device__ __forceinline__ double2 bj_exchange(BjShared& sh, unsigned& xcount, unsigned rank, int nslots, int slot, int lane, double x, double y) {
+  const unsigned b = xcount & 1u, par = (xcount >> 1) & 1u;
+  ++xcount;
+  const unsigned mb = clus::smem_u32(&sh.mbar[b]);
+  if (lane == 0 && slot < nslots) {
+    sh.xbuf[b][rank][slot] = make_double2(x, y);
+    const unsigned la = clus::smem_u32(&sh.xbuf[b][rank][slot]);
+#pragma unroll
+    for (unsigned p = 1; p < (unsigned)BJ_C; ++p) {
+      const unsigned peer = (rank + p) % BJ_C;
+      clus::st_async_v2(clus::mapa(la, peer), x, y, clus::mapa(mb, peer));
+    }
+  }
+  clus::mbar_wait(mb, par);
+  if (threadIdx.x == 0) clus::mbar_expect(mb, (unsigned)((BJ_C - 1) * nslots * 16));      // re-arm for the exchange after the next
+  __syncwarp();                                                                             // (own partial: written by lane 0 of the slot)
+  double sx = 0.0, sy = 0.0;
+  if (slot < nslots) {
+#pragma unroll
+    for (int r = 0; r < BJ_C; ++r) { const double2 v = sh.xbuf[b][r][slot]; sx += v.x; sy += v.y; }
+  }
+  return make_double2(sx, sy);
+}
+
+// TPP lanes per pair (8 while the block has at most 128 rows: 64 pair slots x 8 lanes; 4 beyond that), EPL columns per lane
+template <int TPP, int EPL>
+__device__ void bj_run(DecompBuffers& b, const DecompBlock& B, int keff, int ldz, double F, cplx* __restrict__ Rs, BjShared& sh) {
+  const int tid = threadIdx.x, slot = tid / TPP, lane = tid % TPP;
+  const unsigned rank = clus::cluster_rank();
+  const int nv = B.nv;
+  const int w = (nv + BJ_C - 1) / BJ_C;                // columns of this CTA's slice: [c0, c0 + w) clipped to nv
+  const int c0 = (int)rank * w;
+  // row stride of the slice in shared memory, = 4 (mod 8) complex numbers: the lanes of a pair read 16 B each from consecutive
+  // addresses, the pairs of a warp sit in consecutive rows, and a stride of 0 (mod 128 B) would put them all on the same banks
+  constexpr int WP = (TPP * EPL) % 8 == 0 ? TPP * EPL + 4 : ((TPP * EPL) % 8 == 4 ? TPP * EPL : TPP * EPL + (12 - (TPP * EPL) % 8) % 8);
+  const cplx* Yb = b.ywork + b.ywork_half + B.ws_off;
+  cplx* Ya = b.ywork + B.ws_off;
+  const short* perm = reinterpret_cast<const short*>(b.scratch_d + 4 * NV_MAX) + B.p_off;
+  const double thr = F * DEFLATE_REL;
+  unsigned xcount = 0;
+  for (int e = tid; e < keff * WP; e += BJ_THREADS) {  // slice of R -> shared memory (zero padded)
+    const int r = e / WP, cl = e % WP, c = c0 + cl;
+    Rs[e] = (cl < w && c < nv) ? Yb[(size_t)r * ldz + c] : make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  const int npad = (keff + 1) & ~1, nslots = npad >> 1, mm = npad - 1;
+  cplx ra[EPL], rb[EPL];
+  auto load_row = [&](cplx (&r)[EPL], int row) {
+    const cplx* z = Rs + (row >= 0 ? row : 0) * WP + lane;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) r[e] = row >= 0 ? z[TPP * e] : make_double2(0.0, 0.0);
+  };
+  auto store_row = [&](const cplx (&r)[EPL], int row) {
+    if (row < 0) return;
+    cplx* z = Rs + row * WP + lane;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) z[TPP * e] = r[e];
+  };
+  auto lanes_sum = [&](double v) {
+#pragma unroll
+    for (int o = TPP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+  auto exact_norms = [&]() {                           // slot s takes rows 2s and 2s+1
+    const int x = 2 * slot < keff ? 2 * slot : -1, y = 2 * slot + 1 < keff ? 2 * slot + 1 : -1;
+    load_row(ra, x);
+    load_row(rb, y);
+    double sa = 0.0, sb = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) { sa += ra[e].x * ra[e].x + ra[e].y * ra[e].y; sb += rb[e].x * rb[e].x + rb[e].y * rb[e].y; }
+    sa = lanes_sum(sa); sb = lanes_sum(sb);
+    const double2 t = bj_exchange(sh, xcount, rank, nslots, slot, lane, sa, sb);
+    if (lane == 0) { if (x >= 0) sh.nrm[x] = t.x; if (y >= 0) sh.nrm[y] = t.y; }
+  };
+  bool converged = keff < 2;
+#ifdef OCMPS_JAC_TRACE
+  long long tq[3] = {0, 0, 0};
+  long long tql = clock64();
+  int nrounds = 0;
+#define BJ_MARK(i) { const long long tn = clock64(); tq[i] += tn - tql; tql = tn; }
+#else
+#define BJ_MARK(i)
+#endif
+  for (int sweep = 0; sweep < JAC_MAX_SWEEPS && !converged; ++sweep) {
+    exact_norms();
+    if (tid == 0) { sh.rot = 0; sh.big = 0; }
+    __syncthreads();
+    for (int R = 0; R < npad - 1; ++R) {
+      // round-robin pairing: slot k plays p = (R + k) mod (npad-1) against q = (R - k) mod (npad-1); slot 0 plays the fixed row
+      int p = -1, q = -1;
+      if (slot < nslots) {
+        p = R + slot; if (p >= mm) p -= mm;
+        q = R - slot; if (q < 0) q += mm;
+        if (slot == 0) q = npad - 1;
+        if (p > q) { const int t = p; p = q; q = t; }
+        if (q >= keff) { p = -1; q = -1; }
+      }
+      const bool act = p >= 0;
+      load_row(ra, p);
+      load_row(rb, q);
+      const double aa = act ? sh.nrm[p] : 0.0, bb = act ? sh.nrm[q] : 0.0;
+      double c0r = 0.0, c0i = 0.0, c1r = 0.0, c1i = 0.0;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const double pr = ra[e].x * rb[e].x + ra[e].y * rb[e].y;      // conj(a) * b
+        const double pi = ra[e].x * rb[e].y - ra[e].y * rb[e].x;
+        if (e & 1) { c1r += pr; c1i += pi; } else { c0r += pr; c0i += pi; }
+      }
+      const double pre = lanes_sum(c0r + c1r), pim = lanes_sum(c0i + c1i);
+      BJ_MARK(0)
+      const double2 cc = bj_exchange(sh, xcount, rank, nslots, slot, lane, pre, pim);
+      BJ_MARK(1)
+      if (act) {
+        const double cre = cc.x, cim = cc.y;
+        const double c2 = cre * cre + cim * cim;
+        if (aa <= thr || bb <= thr) {
+          if (aa <= thr && aa > 0.0) {
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) ra[e] = make_double2(0.0, 0.0);
+            store_row(ra, p);
+            if (lane == 0) sh.nrm[p] = 0.0;
+          }
+          if (bb <= thr && bb > 0.0) {
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) rb[e] = make_double2(0.0, 0.0);
+            store_row(rb, q);
+            if (lane == 0) sh.nrm[q] = 0.0;
+          }
+        } else if (c2 > JAC_TOL2 * aa * bb) {
+          // same angle formulas as jac_rotate (two rsqrt, no division)
+          const double dd = 0.5 * (bb - aa);
+          const double xh = dd * dd + c2;
+          const double ih = rsqrt(xh);
+          const double h = xh * ih;
+          const double sdh = fabs(dd) + h;
+          const double wv = rsqrt(2.0 * h * sdh);
+          const double cs = sdh * wv;
+          const double sgw = dd >= 0.0 ? wv : -wv;
+          const double sr = sgw * cre, si = sgw * cim;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) {
+            const cplx u = ra[e], v = rb[e];
+            ra[e] = make_double2(cs * u.x - (sr * v.x + si * v.y), cs * u.y - (sr * v.y - si * v.x));   // cs a - conj(sigma) b
+            rb[e] = make_double2(cs * v.x + (sr * u.x - si * u.y), cs * v.y + (sr * u.y + si * u.x));   // sigma a + cs b
+          }
+          store_row(ra, p);
+          store_row(rb, q);
+          if (lane == 0) {
+            const double trr = c2 * (sgw * wv) * (2.0 * h);
+            const double a1 = aa - trr, b1 = bb + trr;
+            sh.nrm[p] = a1 > 0.0 ? a1 : 0.0;
+            sh.nrm[q] = b1 > 0.0 ? b1 : 0.0;
+            sh.rot = 1;
+            if (c2 > 1e-16 * aa * bb) sh.big = 1;
+          }
+        }
+      }
+      __syncthreads();
+      BJ_MARK(2)
+#ifdef OCMPS_JAC_TRACE
+      ++nrounds;
+#endif
+    }
+    converged = (sh.rot == 0) || (sh.big == 0);
+    __syncthreads();
+    if (!converged && sweep == JAC_MAX_SWEEPS - 1 && tid == 0 && rank == 0) atomicOr(b.status, OCMPS_ST_NOCONV);
+    if (tid == 0 && rank == 0) { atomicAdd(&g_jac_dbg[0], 1ull); atomicMax(&g_jac_dbg[2], (unsigned long long)(sweep + 1)); if (nv >= 64) atomicAdd(&g_jac_dbg[3], 1ull); if (nv >= 64 && sweep == 0) atomicAdd(&g_jac_dbg[4], 1ull); }
+  }
+#ifdef OCMPS_JAC_TRACE
+  if (tid == 0 && rank == 0 && nv >= 24 && nrounds > 0)
+    printf("JTB nv %d keff %d EPL %d rounds %d per round: load+dot %lld exchange %lld rotate+sync %lld\n", nv, keff, EPL, nrounds, tq[0] / nrounds, tq[1] / nrounds,
+           tq[2] / nrounds);
+#endif
+  // spectrum + normalised right vectors Z[j][physical vector]: every CTA writes its columns
+  exact_norms();
+  __syncthreads();
+  for (int v = slot; v < nv; v += BJ_THREADS / TPP) {
+    if (v < keff) {
+      const double sq = sh.nrm[v];
+      const double inv = sq > 0.0 ? rsqrt(sq) : 0.0;
+      for (int cl = lane; cl < w; cl += TPP) {
+        const int c = c0 + cl;
+        if (c < nv) { const cplx u = Rs[v * WP + cl]; Ya[(size_t)v * nv + (int)perm[c]] = make_double2(u.x * inv, u.y * inv); }
+      }
+      if (lane == 0 && rank == 0) b.P[B.p_off + v] = sq;
+    } else if (lane == 0 && rank == 0) {
+      b.P[B.p_off + v] = 0.0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(BJ_THREADS) jacobi_big_kernel(DecompArgs a, DecompBuffers b) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ BjShared sh;
+  const DecompWork* w = b.dw;
+  const int blk = blockIdx.x / BJ_C;
+  // (uniform over the cluster: all CTAs of a cluster see the same block and the same hand-over flag)
+  if (blk >= w->nblocks) return;
+  const int* hK = reinterpret_cast<const int*>(b.scratch_d + 7 * NV_MAX + OCMPS_MAX_BLK);
+  const int keff = hK[OCMPS_MAX_BLK + blk];
+  if (keff < 0) return;                                  // not handed over to this kernel
+  const int ldz = hK[2 * OCMPS_MAX_BLK + blk];
+  const DecompBlock B = w->blk[blk];
+  const double F = (b.scratch_d + 7 * NV_MAX)[blk];
+  const int tid = threadIdx.x;
+  const int nslots = ((keff + 1) & ~1) >> 1;
+  if (tid == 0) {
+    clus::mbar_init(clus::smem_u32(&sh.mbar[0]), 1);
+    clus::mbar_init(clus::smem_u32(&sh.mbar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    clus::mbar_expect(clus::smem_u32(&sh.mbar[0]), (unsigned)((BJ_C - 1) * nslots * 16));
+    clus::mbar_expect(clus::smem_u32(&sh.mbar[1]), (unsigned)((BJ_C - 1) * nslots * 16));
+  }
+  __syncthreads();
+  clus::cluster_sync();
+  const long long t0 = clock64();
+  cplx* Rs = reinterpret_cast<cplx*>(smem_raw);
+  const int wcols = (B.nv + BJ_C - 1) / BJ_C;
+  if (keff <= BJ_THREADS / 8 * 2) {                      // at most 128 rows: 8 lanes per pair, <= 4 columns per lane
+    switch ((wcols + 7) / 8) {
+      case 1: bj_run<8, 1>(b, B, keff, ldz, F, Rs, sh); break;
+      case 2: bj_run<8, 2>(b, B, keff, ldz, F, Rs, sh); break;
+      case 3: bj_run<8, 3>(b, B, keff, ldz, F, Rs, sh); break;
+      default: bj_run<8, 4>(b, B, keff, ldz, F, Rs, sh); break;
+    }
+  } else {
+    switch ((wcols + 3) / 4) {
+      case 1: bj_run<4, 1>(b, B, keff, ldz, F, Rs, sh); break;
+      case 2: bj_run<4, 2>(b, B, keff, ldz, F, Rs, sh); break;
+      case 3: bj_run<4, 3>(b, B, keff, ldz, F, Rs, sh); break;
+      case 4: bj_run<4, 4>(b, B, keff, ldz, F, Rs, sh); break;
+      case 5: bj_run<4, 5>(b, B, keff, ldz, F, Rs, sh); break;
+      case 6: bj_run<4, 6>(b, B, keff, ldz, F, Rs, sh); break;
+      case 7: bj_run<4, 7>(b, B, keff, ldz, F, Rs, sh); break;
+      default: bj_run<4, 8>(b, B, keff, ldz, F, Rs, sh); break;
+    }
+  }
+  clus::cluster_sync();                                   // no CTA may exit while a peer can still send to it
+  if (tid == 0 && clus::cluster_rank() == 0) {
+    atomicAdd(&g_jac_dbg[1], 1ull);
+    const long long t1 = clock64();
+    if (B.nv >= 64) { atomicAdd(&g_jac_dbg[6], (unsigned long long)(t1 - t0)); atomicAdd(&g_jac_dbg[7], (unsigned long long)(t1 - t0)); }
+#ifdef OCMPS_JAC_TRACE
+    if (B.nv >= 24) printf("JT3 kind %d blk %d nv %d keff %d jac %lld\n", a.kind, blk, B.nv, keff, (long long)(t1 - t0));
+#endif
   }
 }
 
@@ -1472,15 +2066,44 @@ void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_
     cudaFuncSetAttribute(jacobi_blocks_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(build_factors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cudaFuncSetAttribute(jacobi_rot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(JAC_BLOCKED_ROWS * 16 * JAC_EPL * sizeof(cplx)));
+    cudaFuncSetAttribute(jacobi_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BJ_MAX_ROWS * (BJ_TPP * BJ_MAX_EPL + 4) * sizeof(cplx)));
+    cudaFuncSetAttribute(qr_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((32 * BJ_MAX_ROWS + BJ_MAX_ROWS) * sizeof(cplx)));
     g_jac_attr_set[dev] = true;
   }
   }
-  jacobi_blocks_kernel<true, true><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
-  if (long_rows) jacobi_blocks_kernel<true, false><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
-  if (need_global) jacobi_blocks_kernel<false, false><<<nblk_launch, JAC_THREADS, 0, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
+  // Blocks beyond the register-resident rotation kernel (more than 64 rows of R, or rows longer than 128) exist only when the
+  // capacities allow them; from chi_cap >= 112 on they are finished by the cluster kernel instead of the generic loops.
+  static const bool big_env = [] { const char* e = getenv("OCMPS_BIG_CLUSTER"); return !(e && e[0] == '0'); }();
+  const int big_on = (big_env && max_rows >= BJ_MIN_CAP) ? 1 : 0;
+  jacobi_blocks_kernel<true, true><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol, big_on);
+  if (long_rows) jacobi_blocks_kernel<true, false><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol, big_on);
+  if (need_global) jacobi_blocks_kernel<false, false><<<nblk_launch, JAC_THREADS, 0, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol, big_on);
   // (after ALL first-stage variants: each of them publishes the hand-over flag of the blocks it owns)
-  (void)max_rows;
+  if (big_on) {      // cluster QR of the blocks the register-cached kernel does not take (before the Jacobi kernels read the hand-over table)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nblk_launch * BJ_C, 1, 1);
+    cfg.blockDim = dim3(BJ_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)(32 * BJ_MAX_ROWS + BJ_MAX_ROWS) * sizeof(cplx);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = BJ_C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, qr_big_kernel, a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
+  }
   jacobi_rot_kernel<<<nblk_launch, JAC_THREADS, JAC_BLOCKED_ROWS * 16 * JAC_EPL * sizeof(cplx), s>>>(a, b);
+  if (big_on) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nblk_launch * BJ_C, 1, 1);
+    cfg.blockDim = dim3(BJ_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)BJ_MAX_ROWS * (BJ_TPP * BJ_MAX_EPL + 4) * sizeof(cplx);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = BJ_C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, jacobi_big_kernel, a, b);
+  }
 }
 
 void launch_truncate(const DecompArgs& a, const DecompBuffers& b, const TruncParams& tp, cudaStream_t s) {
