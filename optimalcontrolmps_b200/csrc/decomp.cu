@@ -520,7 +520,10 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   const int ldpad = ((nv + 15) >> 4) << 4;
   const bool can_cache = nv <= 16 * JAC_EPL && (nv < len ? nv : len) * ldpad <= smem_elems;
   if (fits != SMEM || (SMEM && can_cache != CACHED)) return;   // another instantiation handles this block
+  const int gram_on = big_on & 2;
+  big_on &= 1;
   if (big_on && !(SMEM && CACHED) && nv <= BJ_MAX_ROWS && len <= BJ_MAX_ROWS) return;   // taken by qr_big_kernel (cluster)
+  if (SMEM && CACHED && gram_on && reinterpret_cast<const int*>(b.scratch_d + 7 * NV_MAX + OCMPS_MAX_BLK)[3 * OCMPS_MAX_BLK + blockIdx.x]) return;   // finished by gram_chol_kernel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = JAC_THREADS / 32;
   const int half = lane >> 4, hl = lane & 15;
   cplx* Ya = b.ywork + B.ws_off;                       // region A: final Z (k x nv, physical vector order)
@@ -887,6 +890,269 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
       if (lane == 0) b.P[B.p_off + v] = s;
     } else if (lane == 0) {
       b.P[B.p_off + v] = 0.0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gate decompositions, first half: Gram matrix on the FP64 tensor cores + pivoted Cholesky (instead of the Householder QR)
+// ------------------------------------------------------------------------------------------------
+// The reference truncates with denmatDecomp, i.e. it diagonalises the Gram matrix theta.theta^H of every charge block
+// (SURVEY A.2); a spectrum that is exact relative to the block's weight (absolute accuracy ~1e-16 F) is therefore all
+// the reference itself has.  For the gate decompositions the triangular factor the Jacobi rotations work on is obtained
+// the same way here: G = <v_i|v_j> of the block's vectors is accumulated with DMMA (mma.sync m8n8k4.f64, 4 real products
+// per complex k4-step) straight from the gathered block in shared memory, and a Cholesky factorisation with diagonal
+// pivoting G = R^H R yields the same R (rows in pivot order, trailing weight test on the pivot) the Householder QR with
+// column pivoting would: 62 left-looking steps of one barrier each (every warp finds the pivot redundantly from the running
+// diagonal; four lanes per vector form its entry of the new row of R from the earlier rows, which are kept in the dead rows of G)
+// instead of 62 Householder steps of ~4 kclk.  The centre moves (psi.position(), Cutoff 1e-16) keep the QR: their
+// rank decisions sit at the rounding level of a Gram matrix.  Blocks this kernel finishes are flagged in hG and skipped
+// by jacobi_blocks_kernel<true, true>, which follows on the same stream and still takes what is left (blocks whose R
+// has more than JAC_BLOCKED_ROWS rows, shapes that do not fit).
+constexpr int GC_SMEM_BYTES = 220 * 1024;
+__host__ __device__ __forceinline__ int gc_ldy(int len) { int l = (len + 3) & ~3; if ((l & 7) == 0) l += 4; return l; }   // = 4 (mod 8): conflict-free fragment loads
+__host__ __device__ __forceinline__ int gc_ldg(int nvp) { return nvp | 1; }
+
+__device__ __forceinline__ void gc_dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+constexpr int GC_MAX_NV = 96;             // 12 x 12 tiles: at most 5 of the 78 upper tiles per warp (their accumulators live in registers)
+constexpr int GC_TILES_PER_WARP = ((GC_MAX_NV / 8) * (GC_MAX_NV / 8 + 1) / 2 + JAC_THREADS / 32 - 1) / (JAC_THREADS / 32);
+
+__global__ void __launch_bounds__(JAC_THREADS) gram_chol_kernel(DecompArgs a, DecompBuffers b, int smem_elems_qr, int gc_elems, double rank_tol) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ short s_posof[GC_MAX_NV], s_order[GC_MAX_NV], s_posphys[GC_MAX_NV];
+  __shared__ double s_rdiag[2 * GC_MAX_NV];
+  __shared__ int s_rowoff[GC_MAX_NV];
+  __shared__ unsigned long long s_cand[2][JAC_THREADS / 32];
+  const DecompWork* w = b.dw;
+  if ((int)blockIdx.x >= w->nblocks) return;
+  const DecompBlock B = w->blk[blockIdx.x];
+  const int nv = B.nv, len = B.len, ld = w->ld, mode = w->mode;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* hF = b.scratch_d + 7 * NV_MAX;
+  int* hK = reinterpret_cast<int*>(b.scratch_d + 7 * NV_MAX + OCMPS_MAX_BLK);
+  int* hB = hK + OCMPS_MAX_BLK;
+  int* hS = hB + OCMPS_MAX_BLK;
+  int* hG = hS + OCMPS_MAX_BLK;
+  const int nvp = (nv + 7) & ~7, ldy = gc_ldy(len), ldg = gc_ldg(nvp);
+  {   // only blocks the register-cached QR instantiation would take, and only if the block and its Gram matrix fit
+    const bool fits = nv * len <= smem_elems_qr && nv <= JAC_NV_SMEM;
+    const int ldpad = ((nv + 15) >> 4) << 4;
+    const bool can_cache = nv <= 16 * JAC_EPL && (nv < len ? nv : len) * ldpad <= smem_elems_qr;
+    if (!(fits && can_cache) || nv > GC_MAX_NV || nvp * ldy > gc_elems || nvp * ldg > gc_elems) {
+      if (tid == 0) hG[blockIdx.x] = 0;
+      return;
+    }
+  }
+  const long long t_start = clock64();
+  cplx* Y = reinterpret_cast<cplx*>(smem_raw);         // gathered block, Y[v][c], rows padded to nvp, components to a multiple of 4
+  cplx* G = Y;                                          // the Gram matrix takes the place of the block once it is accumulated
+  const int* vidx = b.vec_idx + B.vec_off;
+  const int* cidx = b.comp_idx + B.comp_off;
+  const int len4 = (len + 3) & ~3;
+  for (int e = tid; e < nvp * ldy; e += JAC_THREADS) Y[e] = make_double2(0.0, 0.0);
+  __syncthreads();
+  if (mode == 0) {
+    for (int e = tid; e < nv * len; e += JAC_THREADS) {
+      const int c = e / nv, v = e % nv;
+      Y[v * ldy + c] = a.X[(size_t)cidx[c] * ld + vidx[v]];
+    }
+  } else {
+    for (int e = tid; e < nv * len; e += JAC_THREADS) {
+      const int v = e / len, c = e % len;
+      Y[v * ldy + c] = a.X[(size_t)vidx[v] * ld + cidx[c]];
+    }
+  }
+  for (int i = tid; i < GC_MAX_NV; i += JAC_THREADS) s_posof[i] = -1;
+  __syncthreads();
+  // ---- Gram matrix, upper triangle of 8x8 tiles; the accumulators stay in registers until every warp is done with Y ----
+  const int nt = nvp >> 3, ntiles = nt * (nt + 1) / 2;
+  const int g = lane >> 2, t = lane & 3;
+  double acc[GC_TILES_PER_WARP][4];
+  auto tile_of = [&](int e, int& ti, int& tj) { ti = 0; while (e >= nt - ti) { e -= nt - ti; ++ti; } tj = ti + e; };
+#pragma unroll
+  for (int sl = 0; sl < GC_TILES_PER_WARP; ++sl) {
+    acc[sl][0] = acc[sl][1] = acc[sl][2] = acc[sl][3] = 0.0;
+    const int e = warp + (JAC_THREADS / 32) * sl;
+    if (e < ntiles) {
+      int ti, tj;
+      tile_of(e, ti, tj);
+      const cplx* ya = Y + (ti * 8 + g) * ldy + t;
+      const cplx* yb = Y + (tj * 8 + g) * ldy + t;
+      double cr0 = 0.0, cr1 = 0.0, ci0 = 0.0, ci1 = 0.0;
+      for (int k4 = 0; k4 < len4; k4 += 4) {
+        const cplx av = ya[k4], bv = yb[k4];
+        gc_dmma(cr0, cr1, av.x, bv.x);                 // Re: yr yr' + yi yi'
+        gc_dmma(cr0, cr1, av.y, bv.y);
+        gc_dmma(ci0, ci1, av.x, bv.y);                 // Im: yr yi' - yi yr'
+        gc_dmma(ci0, ci1, -av.y, bv.x);
+      }
+      acc[sl][0] = cr0; acc[sl][1] = cr1; acc[sl][2] = ci0; acc[sl][3] = ci1;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int sl = 0; sl < GC_TILES_PER_WARP; ++sl) {
+    const int e = warp + (JAC_THREADS / 32) * sl;
+    if (e < ntiles) {
+      int ti, tj;
+      tile_of(e, ti, tj);
+      cplx* gp = G + (ti * 8 + g) * ldg + tj * 8 + 2 * t;
+      gp[0] = make_double2(acc[sl][0], acc[sl][2]);
+      gp[1] = make_double2(acc[sl][1], acc[sl][3]);
+    }
+  }
+  __syncthreads();
+  // block weight F = trace(G): the same bits in every warp (fixed order)
+  double F;
+  {
+    double part = 0.0;
+    for (int i = lane; i < nv; i += 32) part += G[i * ldg + i].x;
+    F = warp_sum(part);
+  }
+  const double rtol_abs = F * (rank_tol > 1e-15 ? rank_tol : 1e-15);      // a Gram matrix resolves nothing below ~1e-16 F
+  const long long t_qr0 = clock64();
+  // ---- Cholesky with diagonal pivoting, left-looking; vectors keep their physical index ----
+  // Step j: every warp finds the pivot p (largest remaining diagonal) redundantly; row j of R,
+  //   r_j[c] = (G[p][c] - sum_{m<j} conj(R[m][p]) R[m][c]) / sqrt(d_p)     for the vectors c still in play,
+  // is computed by four lanes per vector (every fourth earlier row each) and stored IN the row p of G: that row and the
+  // column p are dead from now on (G itself is never updated, only the diagonal d is downdated), and what later steps
+  // need of G -- row / column p' of the vectors still in play -- lives in rows that have not been overwritten.
+  constexpr unsigned long long KEY_POS = 2047ull;
+  const int kmax = nv < len ? nv : len;
+  double* dgl = s_rdiag + GC_MAX_NV;                     // running diagonal d[i] (second half of s_rdiag)
+  const int col = tid >> 2, sub = tid & 3;               // vector of this lane group, its share of the earlier rows
+  const bool has_cols = warp * 8 < nv;                   // (warp uniform) warps without vectors only follow the pivots
+  bool alive = col < nv;
+  double dcol = 0.0;
+  auto key_of = [&](double dd, int i) -> unsigned long long {
+    return dd > 0.0 ? (((unsigned long long)__double_as_longlong(dd) & ~KEY_POS) | (KEY_POS - (unsigned long long)i)) : 0ull;
+  };
+  // pivot candidates: the best (diagonal bits | 2047 - index) key of every warp's vectors, double buffered over the steps
+  auto publish = [&](int buf, unsigned long long key) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o); key = k2 > key ? k2 : key; }
+    if (lane == 0) s_cand[buf][warp] = key;
+  };
+  if (alive && sub == 0) { dcol = G[col * ldg + col].x; dgl[col] = dcol; }
+  if (has_cols) publish(0, (alive && sub == 0) ? key_of(dcol, col) : 0ull);
+  else if (lane == 0) { s_cand[0][warp] = 0ull; s_cand[1][warp] = 0ull; }
+  __syncthreads();
+  int keff = 0;
+#ifdef OCMPS_JAC_TRACE
+  long long tg[5] = {0, 0, 0, 0, 0};
+  long long tgl = clock64();
+#define GC_MARK(i) { const long long tn = clock64(); tg[i] += tn - tgl; tgl = tn; }
+#else
+#define GC_MARK(i)
+#endif
+  for (int j = 0; j < kmax; ++j) {
+    unsigned long long key = lane < JAC_THREADS / 32 ? s_cand[j & 1][lane] : 0ull;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) { const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o); key = k2 > key ? k2 : key; }
+    key = __shfl_sync(0xffffffffu, key, 0);
+    if (key == 0ull) break;
+    const int p = (int)(KEY_POS - (key & KEY_POS));
+    const double dp = dgl[p];
+    if (!(dp > rtol_abs)) break;                        // numerical rank reached (uniform: every warp sees the same bits)
+    keff = j + 1;
+    if (tid == 0) { s_order[j] = (short)p; s_rowoff[j] = p * ldg; s_posof[p] = (short)j; }
+    GC_MARK(0)
+    if (has_cols) {
+      const double inv = rsqrt(dp);
+      if (tid == 0) s_rdiag[j] = dp * inv;
+      if (col == p) alive = false;
+      GC_MARK(1)
+      double sr = 0.0, si = 0.0;
+      if (alive) {
+        // four earlier rows in flight per lane (the loads of one row depend on nothing but the row offset)
+        for (int m = sub; m < j; m += 16) {
+          cplx x[4], y[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int mm = m + 4 * q;
+            x[q] = make_double2(0.0, 0.0); y[q] = make_double2(0.0, 0.0);
+            if (mm < j) { const cplx* rrow = G + s_rowoff[mm]; x[q] = rrow[p]; y[q] = rrow[col]; }
+          }
+          double ar = 0.0, ai = 0.0, br = 0.0, bi = 0.0;
+          ar += x[0].x * y[0].x + x[0].y * y[0].y;  ai += x[0].x * y[0].y - x[0].y * y[0].x;     // conj(R[m][p]) R[m][c]
+          br += x[1].x * y[1].x + x[1].y * y[1].y;  bi += x[1].x * y[1].y - x[1].y * y[1].x;
+          ar += x[2].x * y[2].x + x[2].y * y[2].y;  ai += x[2].x * y[2].y - x[2].y * y[2].x;
+          br += x[3].x * y[3].x + x[3].y * y[3].y;  bi += x[3].x * y[3].y - x[3].y * y[3].x;
+          sr += ar + br; si += ai + bi;
+        }
+      }
+      sr += __shfl_xor_sync(0xffffffffu, sr, 1); si += __shfl_xor_sync(0xffffffffu, si, 1);
+      sr += __shfl_xor_sync(0xffffffffu, sr, 2); si += __shfl_xor_sync(0xffffffffu, si, 2);
+      GC_MARK(2)
+      unsigned long long mykey = 0ull;
+      if (alive && sub == 0) {
+        const cplx gv = col > p ? G[p * ldg + col] : G[col * ldg + p];
+        const double gr = gv.x, gi = col > p ? gv.y : -gv.y;
+        const double rr = (gr - sr) * inv, ri = (gi - si) * inv;
+        G[p * ldg + col] = make_double2(rr, ri);
+        const double dn = dcol - (rr * rr + ri * ri);
+        dcol = dn > 0.0 ? dn : 0.0;
+        dgl[col] = dcol;
+        mykey = key_of(dcol, col);
+      }
+      publish((j + 1) & 1, mykey);
+      GC_MARK(3)
+    }
+    __syncthreads();
+    GC_MARK(4)
+  }
+  __syncthreads();
+#ifdef OCMPS_JAC_TRACE
+  if (tid == 0 && nv >= 64 && keff > 0)
+    printf("JTC nv %d keff %d per step: pivot %lld rsqrt %lld dot+reduce %lld tail+publish %lld barrier %lld\n", nv, keff, tg[0] / keff, tg[1] / keff, tg[2] / keff,
+           tg[3] / keff, tg[4] / keff);
+#endif
+  if (keff > JAC_BLOCKED_ROWS) {                        // more rows than the register-resident rotations take: the QR kernel redoes the block
+    if (tid == 0) hG[blockIdx.x] = 0;
+    return;
+  }
+  // positions: picked vectors in pivot order, then the rest in index order
+  if (tid == 0) {
+    for (int j = 0; j < keff; ++j) s_posphys[j] = s_order[j];
+    int q = keff;
+    for (int i = 0; i < nv; ++i) if (s_posof[i] < 0) s_posphys[q++] = (short)i;
+  }
+  __syncthreads();
+  // ---- R (keff x nv, position order, zero-padded stride) -> the Jacobi working set ----
+  const int ldz = ((nv + 15) >> 4) << 4;
+  cplx* Yb = b.ywork + b.ywork_half + B.ws_off;
+  for (int e = tid; e < keff * ldz; e += JAC_THREADS) {
+    const int c = e / ldz, pos = e % ldz;
+    cplx v = make_double2(0.0, 0.0);
+    if (pos == c) v = make_double2(s_rdiag[c], 0.0);
+    else if (pos > c && pos < nv) v = G[(int)s_order[c] * ldg + (int)s_posphys[pos]];
+    Yb[e] = v;
+  }
+  short* gperm = reinterpret_cast<short*>(b.scratch_d + 4 * NV_MAX) + B.p_off;
+  for (int i = tid; i < nv; i += JAC_THREADS) gperm[i] = s_posphys[i];
+  if (tid == 0) {
+    hF[blockIdx.x] = F;
+    hK[blockIdx.x] = keff;
+    hB[blockIdx.x] = -1;
+    hS[blockIdx.x] = ldz;
+    hG[blockIdx.x] = 1;
+    const double nn = (double)len, mmv = (double)nv;
+    atomicAdd(&g_jac_flops[0], 8.0 * nn * nn * mmv + (56.0 / 3.0) * nn * nn * nn);
+    if (blockIdx.x == 0) {
+      const double dn = mode == 0 ? (double)w->n : (double)w->m, dm = mode == 0 ? (double)w->m : (double)w->n;
+      atomicAdd(&g_jac_flops[1], 8.0 * dn * dn * dm + (56.0 / 3.0) * dn * dn * dn);
+    }
+    if (nv >= 64) {
+      const long long t_now = clock64();
+      atomicAdd(&g_jac_dbg[5], (unsigned long long)(t_now - t_qr0));
+      atomicAdd(&g_jac_dbg[7], (unsigned long long)(t_now - t_start));
+#ifdef OCMPS_JAC_TRACE
+      printf("JTG kind %d blk %d nv %d len %d keff %d gather+gram %lld cholesky+out %lld\n", a.kind, (int)blockIdx.x, nv, len, keff,
+             (long long)(t_qr0 - t_start), (long long)(t_now - t_qr0));
+#endif
     }
   }
 }
@@ -2043,7 +2309,7 @@ void profile_read(double* out) {
 }
 
 void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_launch, size_t smem_limit, bool need_global,
-                          bool long_rows, double rank_tol, int max_rows, cudaStream_t s) {
+                          bool long_rows, double rank_tol, int max_rows, int capV, int capC, cudaStream_t s) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof_on) {
     if (g_prof_used == g_prof_events.size()) {
@@ -2068,13 +2334,25 @@ void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_
     cudaFuncSetAttribute(jacobi_rot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(JAC_BLOCKED_ROWS * 16 * JAC_EPL * sizeof(cplx)));
     cudaFuncSetAttribute(jacobi_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BJ_MAX_ROWS * (BJ_TPP * BJ_MAX_EPL + 4) * sizeof(cplx)));
     cudaFuncSetAttribute(qr_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((32 * BJ_MAX_ROWS + BJ_MAX_ROWS) * sizeof(cplx)));
+    cudaFuncSetAttribute(gram_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GC_SMEM_BYTES);
     g_jac_attr_set[dev] = true;
   }
   }
   // Blocks beyond the register-resident rotation kernel (more than 64 rows of R, or rows longer than 128) exist only when the
   // capacities allow them; from chi_cap >= 112 on they are finished by the cluster kernel instead of the generic loops.
   static const bool big_env = [] { const char* e = getenv("OCMPS_BIG_CLUSTER"); return !(e && e[0] == '0'); }();
-  const int big_on = (big_env && max_rows >= BJ_MIN_CAP) ? 1 : 0;
+  int big_on = (big_env && max_rows >= BJ_MIN_CAP) ? 1 : 0;
+  // Gate decompositions get their triangular factor from the Gram matrix (DMMA) + pivoted Cholesky; the QR kernel that follows
+  // only takes the blocks that kernel left (flag bit 1 of big_on).  OCMPS_GRAM=0 keeps the Householder QR everywhere.
+  static const bool gram_env = [] { const char* e = getenv("OCMPS_GRAM"); return !(e && e[0] == '0'); }();
+  if (gram_env && (a.kind == DK_GATE_LEFT || a.kind == DK_GATE_RIGHT)) {
+    const int capVp = (std::min(capV, GC_MAX_NV) + 7) & ~7;
+    size_t gc_bytes = (size_t)std::max(capVp * gc_ldy(capC), capVp * gc_ldg(capVp)) * sizeof(cplx);
+    gc_bytes = std::min(gc_bytes, (size_t)GC_SMEM_BYTES);
+    gram_chol_kernel<<<nblk_launch, JAC_THREADS, gc_bytes, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), (int)(gc_bytes / sizeof(cplx)), rank_tol);
+    big_on |= 2;
+    ++g_ocmps_launches;
+  }
   jacobi_blocks_kernel<true, true><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol, big_on);
   if (long_rows) jacobi_blocks_kernel<true, false><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol, big_on);
   if (need_global) jacobi_blocks_kernel<false, false><<<nblk_launch, JAC_THREADS, 0, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol, big_on);

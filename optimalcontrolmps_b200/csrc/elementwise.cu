@@ -1,5 +1,8 @@
 // Bandwidth-type kernels of the engine: Trotter gate application on the merged two-site tensor,
 // diagonal on-site phases, slice-store copies, transfer-matrix planning / fix-ups, K|psi> expansion.
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
 #include "ocmps_internal.h"
 
 namespace {
@@ -225,6 +228,94 @@ __global__ void unpack_copy_kernel(const cplx* src_base, SitePtrs dst, SiteOffs 
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x) d[e] = s[e];
 }
 
+// ---- slice store through the TMA unit ----
+// A slice is L contiguous site tensors (up to 960 KB each at chi = 100): pure data movement, so no thread touches the data.
+// One elected lane per CTA streams its share of a site through a ring of shared-memory stages with bulk asynchronous copies:
+// global -> shared (cp.async.bulk ... mbarrier::complete_tx::bytes), then shared -> global (cp.async.bulk ... bulk_group) as soon as
+// the stage has landed; a stage is reloaded once the store that reads it has drained (wait_group.read).  Site sizes are read from
+// the device-resident bond dimensions like everywhere else; every piece is a multiple of 16 bytes (complex128) at a 16-byte
+// aligned address.  mode 0: work MPS -> packed buffer, 1: packed buffer -> work MPS, 2: work MPS -> the store slot named by *sp
+// (its last y-slice copies the bond dimensions and the charge labels with ordinary loads and stores).
+namespace tma {
+constexpr int CHUNK = 16384;            // bytes per bulk copy
+constexpr int STAGES = 4;               // ring depth: 64 KB of shared memory per CTA
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+// bounded wait: a copy that never completes sets the status word instead of hanging the device
+__device__ __forceinline__ bool mbar_wait(unsigned mbar, unsigned parity) {
+  for (int spin = 0; spin < (1 << 24); ++spin) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void load(unsigned dst_smem, const void* src, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void store(void* dst, unsigned src_smem, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+}  // namespace tma
+
+__global__ void __launch_bounds__(32) slice_copy_tma_kernel(SitePtrs work, cplx* packed, SiteOffs offs, const int* dims, const int* q, int L, int D,
+                                                            int cap, const StepParams* __restrict__ sp, int mode, int* status) {
+  extern __shared__ __align__(128) unsigned char stage_buf[];
+  __shared__ __align__(8) unsigned long long mbar[tma::STAGES];
+  const int j = blockIdx.y;
+  if (j >= L) {                                            // (mode 2) bond dimensions and charge labels of the slot
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int b = tid; b <= L; b += nt) sp->slot_dims[b] = dims[b];
+    for (int e = tid; e < (L + 1) * cap; e += nt) sp->slot_q[e] = q[e];
+    return;
+  }
+  if (threadIdx.x != 0) return;
+  const long long bytes = (long long)dims[j] * D * dims[j + 1] * (long long)sizeof(cplx);
+  cplx* pk = (mode == 2 ? sp->slot_data : packed) + offs.o[j];
+  const unsigned char* src = reinterpret_cast<const unsigned char*>(mode == 1 ? pk : work.p[j]);
+  unsigned char* dst = reinterpret_cast<unsigned char*>(mode == 1 ? work.p[j] : pk);
+  const long long nchunks = (bytes + tma::CHUNK - 1) / tma::CHUNK;
+  const long long mine = nchunks > (long long)blockIdx.x ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;    // chunks blockIdx.x, + gridDim.x, ...
+  if (mine == 0) return;
+  for (int i = 0; i < tma::STAGES; ++i) tma::mbar_init(tma::smem_u32(&mbar[i]), 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  auto chunk_bytes = [&](long long i) -> unsigned {
+    const long long c = blockIdx.x + i * (long long)gridDim.x;
+    const long long rest = bytes - c * tma::CHUNK;
+    return (unsigned)(rest < tma::CHUNK ? rest : tma::CHUNK);
+  };
+  auto issue_load = [&](long long i) {
+    const int st = (int)(i % tma::STAGES);
+    const long long c = blockIdx.x + i * (long long)gridDim.x;
+    const unsigned nb = chunk_bytes(i);
+    tma::mbar_expect(tma::smem_u32(&mbar[st]), nb);
+    tma::load(tma::smem_u32(stage_buf + (size_t)st * tma::CHUNK), src + c * tma::CHUNK, nb, tma::smem_u32(&mbar[st]));
+  };
+  const long long pre = mine < tma::STAGES ? mine : tma::STAGES;
+  for (long long i = 0; i < pre; ++i) issue_load(i);
+  for (long long i = 0; i < mine; ++i) {
+    const int st = (int)(i % tma::STAGES);
+    if (!tma::mbar_wait(tma::smem_u32(&mbar[st]), (unsigned)((i / tma::STAGES) & 1))) { if (status) atomicOr(status, OCMPS_ST_NOCONV); else __trap(); break; }
+    const long long c = blockIdx.x + i * (long long)gridDim.x;
+    tma::store(dst + c * tma::CHUNK, tma::smem_u32(stage_buf + (size_t)st * tma::CHUNK), chunk_bytes(i));
+    tma::commit();
+    // the stage of chunk i-1 is reloaded (chunk i-1+STAGES) once the store of chunk i-1 has read it; the store of chunk i stays in flight
+    if (i >= 1 && i - 1 + tma::STAGES < mine) {
+      tma::wait_read<1>();
+      issue_load(i - 1 + tma::STAGES);
+    }
+  }
+  tma::wait_all();
+}
+
 // ---- overlaps ----
 __device__ __forceinline__ const cplx* side_site(const OvlSide& s, int z, int site) {
   return s.use_ptrs ? s.ptrs.p[site] : s.base + (long long)(s.slot0 + z) * s.slot_stride + s.offs.o[site];
@@ -442,19 +533,45 @@ void launch_set_step_params(const StepParams& hp, StepParams* dst, cudaStream_t 
   set_step_params_kernel<<<1, 32, 0, s>>>(hp, dst);
 }
 
+// OCMPS_TMA_COPY=1 sends the slice store through the TMA unit (slice_copy_tma_kernel).  Measured on a B200 at the cfg2 shape
+// (14.2 MB per slice, ncu gpu__time_duration): 8.9-9.3 us against 8.1-8.5 us of the plain load/store kernels below -- a copy
+// this short is bound by its launch, the dependent loads of its sizes and one DRAM round trip, not by how the bytes are moved
+// (profiles/r02_results.md) -- so the plain kernels stay the default.
+static bool tma_copy_enabled() {
+  static const bool on = [] { const char* e = getenv("OCMPS_TMA_COPY"); return e && e[0] == '1'; }();
+  return on;
+}
+static void launch_slice_copy_tma(SitePtrs work, cplx* packed, SiteOffs offs, const int* dims, const int* q, int L, int D, int cap,
+                                  int max_site_elems, const StepParams* sp, int mode, int* status, cudaStream_t s) {
+  static std::once_flag once[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::call_once(once[dev & 63], [] {
+    cudaFuncSetAttribute(slice_copy_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tma::CHUNK * tma::STAGES);
+  });
+  const long long max_chunks = ((long long)max_site_elems * (long long)sizeof(cplx) + tma::CHUNK - 1) / tma::CHUNK;
+  // about two CTAs per SM over all sites, at least one chunk per CTA
+  int gx = (int)std::min<long long>(std::max<long long>(max_chunks, 1), std::max(1, (2 * 148 + L - 1) / L));
+  dim3 grid(gx, mode == 2 ? L + 1 : L);
+  slice_copy_tma_kernel<<<grid, 32, tma::CHUNK * tma::STAGES, s>>>(work, packed, offs, dims, q, L, D, cap, sp, mode, status);
+}
+
 void launch_pack_to_slot(SitePtrs src, SiteOffs offs, const int* dims, const int* q, int L, int D, int cap, int max_site_elems,
-                         const StepParams* sp, cudaStream_t s) {
+                         const StepParams* sp, int* status, cudaStream_t s) {
+  if (tma_copy_enabled()) { launch_slice_copy_tma(src, nullptr, offs, dims, q, L, D, cap, max_site_elems, sp, 2, status, s); return; }
   dim3 grid(grid_for(max_site_elems, 256, 64), L + 1);
   pack_to_slot_kernel<<<grid, 256, 0, s>>>(src, offs, dims, q, L, D, cap, sp);
 }
 
-void launch_pack_copy(SitePtrs src, cplx* dst_base, SiteOffs offs, const int* dims, int L, int D, int max_site_elems,
+void launch_pack_copy(SitePtrs src, cplx* dst_base, SiteOffs offs, const int* dims, int L, int D, int max_site_elems, int* status,
                       cudaStream_t s) {
+  if (tma_copy_enabled()) { launch_slice_copy_tma(src, dst_base, offs, dims, nullptr, L, D, 0, max_site_elems, nullptr, 0, status, s); return; }
   dim3 grid(grid_for(max_site_elems, 256, 64), L);
   pack_copy_kernel<<<grid, 256, 0, s>>>(src, dst_base, offs, dims, D);
 }
-void launch_unpack_copy(const cplx* src_base, SitePtrs dst, SiteOffs offs, const int* dims, int L, int D, int max_site_elems,
+void launch_unpack_copy(const cplx* src_base, SitePtrs dst, SiteOffs offs, const int* dims, int L, int D, int max_site_elems, int* status,
                         cudaStream_t s) {
+  if (tma_copy_enabled()) { launch_slice_copy_tma(dst, const_cast<cplx*>(src_base), offs, dims, nullptr, L, D, 0, max_site_elems, nullptr, 1, status, s); return; }
   dim3 grid(grid_for(max_site_elems, 256, 64), L);
   unpack_copy_kernel<<<grid, 256, 0, s>>>(src_base, dst, offs, dims, D);
 }

@@ -540,7 +540,7 @@ void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int c
   rank_tol = std::min(rank_scale * 1e-8, std::max(1e-30, rank_tol));
   const bool long_rows = capV > 128;                   // rows of R longer than the register-cached path handles
   const int max_rows = std::min(capV, capC);           // rows of R of the largest possible block
-  launch_jacobi_blocks(a, db, nblk, smem, need_global, long_rows, rank_tol, max_rows, s);
+  launch_jacobi_blocks(a, db, nblk, smem, need_global, long_rows, rank_tol, max_rows, capV, capC, s);
   g_trace.mark((a.kind == DK_GATE_LEFT || a.kind == DK_GATE_RIGHT) ? TR_SVD_GATE : TR_SVD_ORTH, s);
   launch_truncate(a, db, tp, s);
   g_trace.mark(TR_TRUNC, s);
@@ -734,7 +734,7 @@ int step_enqueue(ocmps_stepper* st, ocmps_mps* m, Workspace* ws, double from, do
   auto body = [&]() {
     run_step_body(st, m, ws, s);
     if (store) {
-      launch_pack_to_slot(m->ptrs(), lay.offs, m->d_dims, m->d_q, lay.L, lay.D, lay.cap, lay.max_site_elems, ws->d_params, s);
+      launch_pack_to_slot(m->ptrs(), lay.offs, m->d_dims, m->d_q, lay.L, lay.D, lay.cap, lay.max_site_elems, ws->d_params, ws->d_status, s);
       g_ocmps_launches += 1;
     }
   };
@@ -812,7 +812,7 @@ int copy_mps_async(ocmps_mps* dst, ocmps_mps* src, cudaStream_t s) {
   if (dst->lay.L != src->lay.L || dst->lay.D != src->lay.D || dst->lay.cap != src->lay.cap)
     return fail(OCMPS_ERR_INVALID, "mps copy: shape mismatch");
   const Layout& lay = src->lay;
-  launch_pack_copy(src->ptrs(), dst->arena[0], lay.offs, src->d_dims, lay.L, lay.D, lay.max_site_elems, s);
+  launch_pack_copy(src->ptrs(), dst->arena[0], lay.offs, src->d_dims, lay.L, lay.D, lay.max_site_elems, nullptr, s);
   g_ocmps_launches += 1;
   for (int j = 0; j < lay.L; ++j) dst->cur[j] = 0;
   CK(cudaMemcpyAsync(dst->d_dims, src->d_dims, sizeof(int) * (lay.L + 1), cudaMemcpyDeviceToDevice, s));
@@ -825,7 +825,7 @@ int store_put_async(ocmps_store* st, int slot, ocmps_mps* m, cudaStream_t s) {
   const Layout& lay = st->lay;
   if (m->lay.L != lay.L || m->lay.D != lay.D || m->lay.cap != lay.cap) return fail(OCMPS_ERR_INVALID, "store/mps shape mismatch");
   if (slot < 0 || slot >= st->nslots) return fail(OCMPS_ERR_INVALID, "slot out of range");
-  launch_pack_copy(m->ptrs(), st->data + (size_t)slot * lay.total, lay.offs, m->d_dims, lay.L, lay.D, lay.max_site_elems, s);
+  launch_pack_copy(m->ptrs(), st->data + (size_t)slot * lay.total, lay.offs, m->d_dims, lay.L, lay.D, lay.max_site_elems, nullptr, s);
   g_ocmps_launches += 1;
   CK(cudaMemcpyAsync(st->dims + (size_t)slot * (lay.L + 1), m->d_dims, sizeof(int) * (lay.L + 1), cudaMemcpyDeviceToDevice, s));
   CK(cudaMemcpyAsync(st->q + (size_t)slot * (lay.L + 1) * lay.cap, m->d_q, sizeof(int) * (size_t)(lay.L + 1) * lay.cap,
@@ -839,7 +839,7 @@ int store_get_async(ocmps_store* st, int slot, ocmps_mps* m, cudaStream_t s) {
   if (slot < 0 || slot >= st->nslots) return fail(OCMPS_ERR_INVALID, "slot out of range");
   for (int j = 0; j < lay.L; ++j) m->cur[j] = 0;
   const int* dims = st->dims + (size_t)slot * (lay.L + 1);
-  launch_unpack_copy(st->data + (size_t)slot * lay.total, m->ptrs(), lay.offs, dims, lay.L, lay.D, lay.max_site_elems, s);
+  launch_unpack_copy(st->data + (size_t)slot * lay.total, m->ptrs(), lay.offs, dims, lay.L, lay.D, lay.max_site_elems, nullptr, s);
   g_ocmps_launches += 1;
   CK(cudaMemcpyAsync(m->d_dims, dims, sizeof(int) * (lay.L + 1), cudaMemcpyDeviceToDevice, s));
   CK(cudaMemcpyAsync(m->d_q, st->q + (size_t)slot * (lay.L + 1) * lay.cap, sizeof(int) * (size_t)(lay.L + 1) * lay.cap,
@@ -960,7 +960,7 @@ int apply_K_async(ocmps_stepper* st, Workspace* ws, ocmps_mps* in, ocmps_mps* ou
   for (int j = 0; j < L; ++j) out->cur[j] = 0;
   copy_bookkeeping_kernel<<<L + 1, 128, 0, s>>>(big->d_dims, big->d_q, lb.cap, out->d_dims, out->d_q, out->lay.cap, L, out->lay.cap,
                                                ws->d_status);
-  launch_pack_copy(big->ptrs(), out->arena[0], out->lay.offs, out->d_dims, L, D, out->lay.max_site_elems, s);
+  launch_pack_copy(big->ptrs(), out->arena[0], out->lay.offs, out->d_dims, L, D, out->lay.max_site_elems, ws->d_status, s);
   g_ocmps_launches += 2;
   out->llim = 0; out->rlim = 2;
   return OCMPS_OK;
@@ -2044,7 +2044,9 @@ static int hessian_run(ocmps_stepper* st, ocmps_mps* psi_init, ocmps_mps* psi_ta
         for (cudaEvent_t e : ev_xiH) cudaStreamWaitEvent(ws->ovl, e, 0);
         S.xiH_waited = true;
       }
-      int lrc = overlaps_async(ws, side_of_store(xiH_store, P.j0), xiH_store->lay, side_of_store(ws->rowstore, P.m * CH), ws->rowstore->lay,
+      const char* skip_env = getenv("OCMPS_HESSIAN_SKIP_OVL");          // timing experiments only: the Hessian is wrong without the overlaps
+      const bool skip_ovl = skip_env && skip_env[0] == '1';
+      int lrc = skip_ovl ? OCMPS_OK : overlaps_async(ws, side_of_store(xiH_store, P.j0), xiH_store->lay, side_of_store(ws->rowstore, P.m * CH), ws->rowstore->lay,
                                P.filled, 0, ws->ovl);
       if (lrc) return lrc;
       if (cudaMemcpyAsync(d_ovl + (size_t)P.row * Nt + P.j0, ws->d_out, sizeof(cplx) * P.filled, cudaMemcpyDeviceToDevice, ws->ovl) != cudaSuccess)

@@ -117,7 +117,7 @@ struct DecompBuffers {
 
 void launch_decomp_setup(const DecompArgs& a, const DecompBuffers& b, cudaStream_t s);
 void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_launch, size_t smem_limit, bool need_global,
-                          bool long_rows, double rank_tol, int max_rows, cudaStream_t s);
+                          bool long_rows, double rank_tol, int max_rows, int capV, int capC, cudaStream_t s);
 void launch_spectrum_entropy(const DecompBuffers& b, double* out, cudaStream_t s);
 void launch_truncate(const DecompArgs& a, const DecompBuffers& b, const TruncParams& tp, cudaStream_t s);
 void launch_build_factors(const DecompArgs& a, const DecompBuffers& b, int cap_k, int cap_vec, int cap_comp, cudaStream_t s);
@@ -135,15 +135,16 @@ void launch_site_phase(cplx* A, const int* dimL, const int* dimR, int D, const S
 void launch_set_step_params(const StepParams& hp, StepParams* dst, cudaStream_t s);
 // pack the work MPS into the store slot named by *sp (data, dims and charge labels)
 void launch_pack_to_slot(SitePtrs src, SiteOffs offs, const int* dims, const int* q, int L, int D, int cap, int max_site_elems,
-                         const StepParams* sp, cudaStream_t s);
+                         const StepParams* sp, int* status, cudaStream_t s);
 void launch_norm_only(const cplx* x, const int* dimL, const int* dimR, int D, double* partial, double* out, int max_elems,
                       cudaStream_t s);
 void launch_normalize_site(cplx* x, const int* dimL, const int* dimR, int D, double* partial, int max_elems, cudaStream_t s);
 
 // packed copies between a work MPS (per-site pointers) and a store slot
-void launch_pack_copy(SitePtrs src, cplx* dst_base, SiteOffs offs, const int* dims, int L, int D, int max_site_elems,
+// (status: device status word of the caller's workspace, or nullptr -- a bulk copy that fails then traps)
+void launch_pack_copy(SitePtrs src, cplx* dst_base, SiteOffs offs, const int* dims, int L, int D, int max_site_elems, int* status,
                       cudaStream_t s);
-void launch_unpack_copy(const cplx* src_base, SitePtrs dst, SiteOffs offs, const int* dims, int L, int D, int max_site_elems,
+void launch_unpack_copy(const cplx* src_base, SitePtrs dst, SiteOffs offs, const int* dims, int L, int D, int max_site_elems, int* status,
                         cudaStream_t s);
 
 // overlaps (transfer matrices).  One "pair" per batch entry.

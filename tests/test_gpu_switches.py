@@ -36,6 +36,8 @@ def default_run():
     ({"OCMPS_HESSIAN_CHUNK": 3}, True),          # same overlaps, batched in passes of 3 slices instead of 32
     ({"OCMPS_FUSED_MERGE": 0}, False),           # dense DMMA GEMM + gate kernel instead of the sector-wise merge+gate
     ({"OCMPS_FUSED_PUSH": 0}, False),            # dense GEMM after a gauge move instead of the push inside build_factors
+    ({"OCMPS_TMA_COPY": 1}, True),               # slice store through TMA bulk copies instead of loads and stores: the same bytes
+    ({"OCMPS_GRAM": 0}, False),                  # Householder QR instead of Gram matrix (DMMA) + pivoted Cholesky in the gate decompositions
 ])
 def test_switch_gives_the_same_result(default_run, env, exact):
     c0, g0, h0, d0 = default_run
