@@ -49,6 +49,16 @@ constexpr int BJ_THREADS = BJ_SLOTS * BJ_TPP;      // 512
 constexpr int BJ_MAX_EPL = 8;             // columns per lane: slices of up to 32 columns, rows of R up to 256 long
 constexpr int BJ_MIN_CAP = 112;           // launched when the capacities allow blocks with at least this many rows
 
+// Gram-matrix path of the gate decompositions (gram_chol_block)
+__host__ __device__ __forceinline__ int gc_ldy(int len) { int l = (len + 3) & ~3; if ((l & 7) == 0) l += 4; return l; }   // = 4 (mod 8): conflict-free fragment loads
+__host__ __device__ __forceinline__ int gc_ldg(int nvp) { return nvp | 1; }
+__device__ __forceinline__ void gc_dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+constexpr int GC_MIN_RANK = 48;           // blocks with fewer vectors or shorter vectors than this keep the Householder QR
+constexpr int GC_MAX_NV = 96;             // 12 x 12 tiles: at most 5 of the 78 upper tiles per warp (their accumulators live in registers)
+constexpr int GC_TILES_PER_WARP = ((GC_MAX_NV / 8) * (GC_MAX_NV / 8 + 1) / 2 + 512 / 32 - 1) / (512 / 32);
+
 // ------------------------------------------------------------------------------------------------
 // setup: charges of rows / columns, block table, sorted index lists
 // ------------------------------------------------------------------------------------------------
@@ -499,6 +509,16 @@ __device__ __forceinline__ int qr_pivoted_cached(QrState& q) {
 // SMEM: the block lives in shared memory (else in the global scratch); CACHED: rows are at most 16*JAC_EPL long and a
 // pair's elements stay in registers between the dot product and the rotation.  A block is handled by exactly one
 // instantiation; splitting them keeps the hot loop of the common case small enough for the instruction caches.
+// the small work arrays of gram_chol_block are the caller's: its QR path does not run on a block that function finishes
+struct GramScratch {
+  short *posof, *order, *posphys;          // GC_MAX_NV entries each
+  double* rdiag;                           // 2 * GC_MAX_NV
+  int* rowoff;                             // GC_MAX_NV
+  unsigned long long (*cand)[32];          // [2][32]
+};
+__device__ bool gram_chol_block(const DecompArgs& a, const DecompBuffers& b, const DecompWork* w, const DecompBlock& B, unsigned char* smem_raw,
+                                int gc_elems, double rank_tol, const GramScratch& gs);
+
 template <bool SMEM, bool CACHED>
 __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a, DecompBuffers b, int smem_elems, double rank_tol, int big_on) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -523,7 +543,14 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
   const int gram_on = big_on & 2;
   big_on &= 1;
   if (big_on && !(SMEM && CACHED) && nv <= BJ_MAX_ROWS && len <= BJ_MAX_ROWS) return;   // taken by qr_big_kernel (cluster)
-  if (SMEM && CACHED && gram_on && reinterpret_cast<const int*>(b.scratch_d + 7 * NV_MAX + OCMPS_MAX_BLK)[3 * OCMPS_MAX_BLK + blockIdx.x]) return;   // finished by gram_chol_kernel
+  if constexpr (SMEM && CACHED) {
+    // gate decompositions: Gram matrix (DMMA) + pivoted Cholesky instead of the Householder QR below (gram_chol_block)
+    if (gram_on) {
+      const GramScratch gs{s_perm, s_permA, s_permB, s_nrm, reinterpret_cast<int*>(s_nrm2), s_cand};
+      if (gram_chol_block(a, b, w, B, smem_raw, smem_elems, rank_tol, gs)) return;
+      __syncthreads();
+    }
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = JAC_THREADS / 32;
   const int half = lane >> 4, hl = lane & 15;
   cplx* Ya = b.ywork + B.ws_off;                       // region A: final Z (k x nv, physical vector order)
@@ -906,46 +933,28 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_blocks_kernel(DecompArgs a
 // column pivoting would: 62 left-looking steps of one barrier each (every warp finds the pivot redundantly from the running
 // diagonal; four lanes per vector form its entry of the new row of R from the earlier rows, which are kept in the dead rows of G)
 // instead of 62 Householder steps of ~4 kclk.  The centre moves (psi.position(), Cutoff 1e-16) keep the QR: their
-// rank decisions sit at the rounding level of a Gram matrix.  Blocks this kernel finishes are flagged in hG and skipped
-// by jacobi_blocks_kernel<true, true>, which follows on the same stream and still takes what is left (blocks whose R
-// has more than JAC_BLOCKED_ROWS rows, shapes that do not fit).
-constexpr int GC_SMEM_BYTES = 220 * 1024;
-__host__ __device__ __forceinline__ int gc_ldy(int len) { int l = (len + 3) & ~3; if ((l & 7) == 0) l += 4; return l; }   // = 4 (mod 8): conflict-free fragment loads
-__host__ __device__ __forceinline__ int gc_ldg(int nvp) { return nvp | 1; }
-
-__device__ __forceinline__ void gc_dmma(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
-
-constexpr int GC_MAX_NV = 96;             // 12 x 12 tiles: at most 5 of the 78 upper tiles per warp (their accumulators live in registers)
-constexpr int GC_TILES_PER_WARP = ((GC_MAX_NV / 8) * (GC_MAX_NV / 8 + 1) / 2 + JAC_THREADS / 32 - 1) / (JAC_THREADS / 32);
-
-__global__ void __launch_bounds__(JAC_THREADS) gram_chol_kernel(DecompArgs a, DecompBuffers b, int smem_elems_qr, int gc_elems, double rank_tol) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ short s_posof[GC_MAX_NV], s_order[GC_MAX_NV], s_posphys[GC_MAX_NV];
-  __shared__ double s_rdiag[2 * GC_MAX_NV];
-  __shared__ int s_rowoff[GC_MAX_NV];
-  __shared__ unsigned long long s_cand[2][JAC_THREADS / 32];
-  const DecompWork* w = b.dw;
-  if ((int)blockIdx.x >= w->nblocks) return;
-  const DecompBlock B = w->blk[blockIdx.x];
+// rank decisions sit at the rounding level of a Gram matrix.  The code is a branch of jacobi_blocks_kernel<true, true> (a kernel of
+// its own cost a launch per decomposition and a third of the throughput of 48 concurrent chains: every CTA of these kernels
+// needs a whole SM); a block it cannot take -- more than 96 vectors, more than JAC_BLOCKED_ROWS rows of R -- falls through to the QR.
+// Opt-in (OCMPS_GRAM=1): parity-green on the whole GPU suite, but not faster than the QR where it matters (see launch_jacobi_blocks).
+// Returns true if the block was finished (R, permutation and hand-over entries written), false if it has to take the QR path:
+// more than GC_MAX_NV vectors, a shape that does not fit the shared memory of this launch, or more than JAC_BLOCKED_ROWS rows of R.
+__device__ bool gram_chol_block(const DecompArgs& a, const DecompBuffers& b, const DecompWork* w, const DecompBlock& B, unsigned char* smem_raw,
+                                int gc_elems, double rank_tol, const GramScratch& gs) {
+  short* const s_posof = gs.posof; short* const s_order = gs.order; short* const s_posphys = gs.posphys;
+  double* const s_rdiag = gs.rdiag;
+  int* const s_rowoff = gs.rowoff;
+  unsigned long long (*const s_cand)[32] = gs.cand;
   const int nv = B.nv, len = B.len, ld = w->ld, mode = w->mode;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* hF = b.scratch_d + 7 * NV_MAX;
   int* hK = reinterpret_cast<int*>(b.scratch_d + 7 * NV_MAX + OCMPS_MAX_BLK);
   int* hB = hK + OCMPS_MAX_BLK;
   int* hS = hB + OCMPS_MAX_BLK;
-  int* hG = hS + OCMPS_MAX_BLK;
   const int nvp = (nv + 7) & ~7, ldy = gc_ldy(len), ldg = gc_ldg(nvp);
-  {   // only blocks the register-cached QR instantiation would take, and only if the block and its Gram matrix fit
-    const bool fits = nv * len <= smem_elems_qr && nv <= JAC_NV_SMEM;
-    const int ldpad = ((nv + 15) >> 4) << 4;
-    const bool can_cache = nv <= 16 * JAC_EPL && (nv < len ? nv : len) * ldpad <= smem_elems_qr;
-    if (!(fits && can_cache) || nv > GC_MAX_NV || nvp * ldy > gc_elems || nvp * ldg > gc_elems) {
-      if (tid == 0) hG[blockIdx.x] = 0;
-      return;
-    }
-  }
+  // Small blocks stay with the QR: its steps are cheaper there (measured: with every block on this path 48 concurrent chains lose a
+  // fifth of their throughput and the L=5 configuration 8 %), and only the largest blocks of a decomposition set its latency.
+  if (nv > GC_MAX_NV || (nv < len ? nv : len) < GC_MIN_RANK || nvp * ldy > gc_elems || nvp * ldg > gc_elems) return false;
   const long long t_start = clock64();
   cplx* Y = reinterpret_cast<cplx*>(smem_raw);         // gathered block, Y[v][c], rows padded to nvp, components to a multiple of 4
   cplx* G = Y;                                          // the Gram matrix takes the place of the block once it is accumulated
@@ -1042,7 +1051,7 @@ __global__ void __launch_bounds__(JAC_THREADS) gram_chol_kernel(DecompArgs a, De
   __syncthreads();
   int keff = 0;
 #ifdef OCMPS_JAC_TRACE
-  long long tg[5] = {0, 0, 0, 0, 0};
+  long long tg[7] = {0, 0, 0, 0, 0, 0, 0};
   long long tgl = clock64();
 #define GC_MARK(i) { const long long tn = clock64(); tg[i] += tn - tgl; tgl = tn; }
 #else
@@ -1053,11 +1062,13 @@ __global__ void __launch_bounds__(JAC_THREADS) gram_chol_kernel(DecompArgs a, De
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) { const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o); key = k2 > key ? k2 : key; }
     key = __shfl_sync(0xffffffffu, key, 0);
+    GC_MARK(5)
     if (key == 0ull) break;
     const int p = (int)(KEY_POS - (key & KEY_POS));
     const double dp = dgl[p];
     if (!(dp > rtol_abs)) break;                        // numerical rank reached (uniform: every warp sees the same bits)
     keff = j + 1;
+    GC_MARK(6)
     if (tid == 0) { s_order[j] = (short)p; s_rowoff[j] = p * ldg; s_posof[p] = (short)j; }
     GC_MARK(0)
     if (has_cols) {
@@ -1107,13 +1118,10 @@ __global__ void __launch_bounds__(JAC_THREADS) gram_chol_kernel(DecompArgs a, De
   __syncthreads();
 #ifdef OCMPS_JAC_TRACE
   if (tid == 0 && nv >= 64 && keff > 0)
-    printf("JTC nv %d keff %d per step: pivot %lld rsqrt %lld dot+reduce %lld tail+publish %lld barrier %lld\n", nv, keff, tg[0] / keff, tg[1] / keff, tg[2] / keff,
-           tg[3] / keff, tg[4] / keff);
+    printf("JTC nv %d keff %d per step: candidates %lld diagonal %lld bookkeeping %lld rsqrt %lld dot+reduce %lld tail+publish %lld barrier %lld\n", nv, keff,
+           tg[5] / keff, tg[6] / keff, tg[0] / keff, tg[1] / keff, tg[2] / keff, tg[3] / keff, tg[4] / keff);
 #endif
-  if (keff > JAC_BLOCKED_ROWS) {                        // more rows than the register-resident rotations take: the QR kernel redoes the block
-    if (tid == 0) hG[blockIdx.x] = 0;
-    return;
-  }
+  if (keff > JAC_BLOCKED_ROWS) return false;            // more rows than the register-resident rotations take: the QR path redoes the block
   // positions: picked vectors in pivot order, then the rest in index order
   if (tid == 0) {
     for (int j = 0; j < keff; ++j) s_posphys[j] = s_order[j];
@@ -1138,7 +1146,6 @@ __global__ void __launch_bounds__(JAC_THREADS) gram_chol_kernel(DecompArgs a, De
     hK[blockIdx.x] = keff;
     hB[blockIdx.x] = -1;
     hS[blockIdx.x] = ldz;
-    hG[blockIdx.x] = 1;
     const double nn = (double)len, mmv = (double)nv;
     atomicAdd(&g_jac_flops[0], 8.0 * nn * nn * mmv + (56.0 / 3.0) * nn * nn * nn);
     if (blockIdx.x == 0) {
@@ -1155,6 +1162,7 @@ __global__ void __launch_bounds__(JAC_THREADS) gram_chol_kernel(DecompArgs a, De
 #endif
     }
   }
+  return true;
 }
 
 // Second half of the block decomposition for the blocks handed over by jacobi_blocks_kernel<true, true>: one-sided
@@ -2334,7 +2342,6 @@ void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_
     cudaFuncSetAttribute(jacobi_rot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(JAC_BLOCKED_ROWS * 16 * JAC_EPL * sizeof(cplx)));
     cudaFuncSetAttribute(jacobi_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BJ_MAX_ROWS * (BJ_TPP * BJ_MAX_EPL + 4) * sizeof(cplx)));
     cudaFuncSetAttribute(qr_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((32 * BJ_MAX_ROWS + BJ_MAX_ROWS) * sizeof(cplx)));
-    cudaFuncSetAttribute(gram_chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GC_SMEM_BYTES);
     g_jac_attr_set[dev] = true;
   }
   }
@@ -2342,17 +2349,12 @@ void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_
   // capacities allow them; from chi_cap >= 112 on they are finished by the cluster kernel instead of the generic loops.
   static const bool big_env = [] { const char* e = getenv("OCMPS_BIG_CLUSTER"); return !(e && e[0] == '0'); }();
   int big_on = (big_env && max_rows >= BJ_MIN_CAP) ? 1 : 0;
-  // Gate decompositions get their triangular factor from the Gram matrix (DMMA) + pivoted Cholesky; the QR kernel that follows
-  // only takes the blocks that kernel left (flag bit 1 of big_on).  OCMPS_GRAM=0 keeps the Householder QR everywhere.
-  static const bool gram_env = [] { const char* e = getenv("OCMPS_GRAM"); return !(e && e[0] == '0'); }();
-  if (gram_env && (a.kind == DK_GATE_LEFT || a.kind == DK_GATE_RIGHT)) {
-    const int capVp = (std::min(capV, GC_MAX_NV) + 7) & ~7;
-    size_t gc_bytes = (size_t)std::max(capVp * gc_ldy(capC), capVp * gc_ldg(capVp)) * sizeof(cplx);
-    gc_bytes = std::min(gc_bytes, (size_t)GC_SMEM_BYTES);
-    gram_chol_kernel<<<nblk_launch, JAC_THREADS, gc_bytes, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), (int)(gc_bytes / sizeof(cplx)), rank_tol);
-    big_on |= 2;
-    ++g_ocmps_launches;
-  }
+  // OCMPS_GRAM=1: the large blocks of the gate decompositions get their triangular factor from the Gram matrix (DMMA) + pivoted
+  // Cholesky inside the register-cached instantiation (flag bit 1 of big_on; gram_chol_block).  Off by default: measured on a B200
+  // the single evaluation is the same within noise (0.862 vs 0.856 evaluations/s) while the 48 concurrent chains of a cfg3
+  // Hessian lose a fifth of their throughput (10.8 s vs 8.8 s) -- profiles/r02_results.md.
+  static const bool gram_env = [] { const char* e = getenv("OCMPS_GRAM"); return e && e[0] == '1'; }();
+  if (gram_env && (a.kind == DK_GATE_LEFT || a.kind == DK_GATE_RIGHT)) big_on |= 2;
   jacobi_blocks_kernel<true, true><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol, big_on);
   if (long_rows) jacobi_blocks_kernel<true, false><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol, big_on);
   if (need_global) jacobi_blocks_kernel<false, false><<<nblk_launch, JAC_THREADS, 0, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol, big_on);

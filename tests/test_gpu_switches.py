@@ -37,7 +37,7 @@ def default_run():
     ({"OCMPS_FUSED_MERGE": 0}, False),           # dense DMMA GEMM + gate kernel instead of the sector-wise merge+gate
     ({"OCMPS_FUSED_PUSH": 0}, False),            # dense GEMM after a gauge move instead of the push inside build_factors
     ({"OCMPS_TMA_COPY": 1}, True),               # slice store through TMA bulk copies instead of loads and stores: the same bytes
-    ({"OCMPS_GRAM": 0}, False),                  # Householder QR instead of Gram matrix (DMMA) + pivoted Cholesky in the gate decompositions
+    ({"OCMPS_GRAM": 1}, False),                  # Gram matrix (DMMA) + pivoted Cholesky instead of the Householder QR in the gate decompositions
 ])
 def test_switch_gives_the_same_result(default_run, env, exact):
     c0, g0, h0, d0 = default_run
@@ -49,3 +49,15 @@ def test_switch_gives_the_same_result(default_run, env, exact):
         assert abs(c1 - c0) <= 1e-12 * abs(c0)
         assert np.max(np.abs(g1 - g0)) <= 1e-11 * np.max(np.abs(g0))
         assert np.max(np.abs(h1 - h0)) <= 1e-10 * np.max(np.abs(h0))
+
+
+def test_gram_path_on_the_full_size_golden():
+    """OCMPS_GRAM=1 only takes charge blocks with at least 48 vectors, which the small goldens above do not have: the complete
+    cfg2 evaluation (every bond dimension of 2 x 201 slices, cost 1e-9, gradient 1e-7) is repeated with the Gram-matrix (DMMA) +
+    pivoted-Cholesky path in a process of its own."""
+    e = dict(os.environ)
+    e["OCMPS_GRAM"] = "1"
+    out = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu",
+                          os.path.join(HERE, "test_gpu_fullsize.py::test_cfg2_full_evaluation_matches_golden")],
+                         env=e, capture_output=True, text=True, timeout=900, cwd=os.path.dirname(HERE))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
