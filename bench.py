@@ -483,7 +483,9 @@ def svd_roofline(lib, fn, peak):
     lib.ocmps_profile_enable(0)
     ms_tot, nl, fl_blk, fl_dense = out4
     ach = fl_blk / (ms_tot * 1e-3) / 1e12 if ms_tot > 0 else 0.0
-    return {"kernel": "jacobi_blocks_kernel + jacobi_rot_kernel", "bound": "latency", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+    return {"kernel": "block SVD launch group: jacobi_blocks_kernel + jacobi_rot_kernel (+ qr_big_kernel + jacobi_big_kernel, the thread-block-"
+                      "cluster pair for blocks beyond one SM, when the bond capacities are >= 112)",
+            "bound": "latency", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
             "frac": ach / peak if peak else None, "traffic": None, "launches": int(nl), "avg_launch_us": ms_tot * 1e3 / max(nl, 1),
             "algorithmic_flops": "block-summed F_gram+F_evd (SURVEY.md 8d)"}
 

@@ -1167,12 +1167,20 @@ __device__ bool gram_chol_block(const DecompArgs& a, const DecompBuffers& b, con
 
 // Second half of the block decomposition for the blocks handed over by jacobi_blocks_kernel<true, true>: one-sided
 // Jacobi on the rows of R with the rows held in registers (jacobi_sweep_blocked), then spectrum and right vectors.
-__global__ void __launch_bounds__(JAC_THREADS) jacobi_rot_kernel(DecompArgs a, DecompBuffers b) {
+__global__ void __launch_bounds__(JAC_THREADS) jacobi_rot_kernel(DecompArgs a, DecompBuffers b, int smem_elems) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_rot, s_big;
   __shared__ double s_nrm[JAC_BLOCKED_ROWS];
   const DecompWork* w = b.dw;
   if ((int)blockIdx.x >= w->nblocks) return;
+  {   // only blocks of the register-cached first stage hand over to this kernel; the hand-over entries of the others may still be
+      // in the making on the cluster stream (launch_jacobi_blocks), so they are told apart by their shape
+    const int nv0 = w->blk[blockIdx.x].nv, len0 = w->blk[blockIdx.x].len;
+    const bool fits = nv0 * len0 <= smem_elems && nv0 <= JAC_NV_SMEM;
+    const int ldpad = ((nv0 + 15) >> 4) << 4;
+    const bool can_cache = nv0 <= 16 * JAC_EPL && (nv0 < len0 ? nv0 : len0) * ldpad <= smem_elems;
+    if (!(fits && can_cache)) return;
+  }
   const int keff = reinterpret_cast<const int*>(b.scratch_d + 7 * NV_MAX + OCMPS_MAX_BLK)[blockIdx.x];
   if (keff < 0) return;                                   // finished by the first kernel
   const DecompBlock B = w->blk[blockIdx.x];
@@ -1772,6 +1780,7 @@ __global__ void __launch_bounds__(BJ_THREADS) jacobi_big_kernel(DecompArgs a, De
   const int blk = blockIdx.x / BJ_C;
   // (uniform over the cluster: all CTAs of a cluster see the same block and the same hand-over flag)
   if (blk >= w->nblocks) return;
+  if (w->blk[blk].nv > BJ_MAX_ROWS || w->blk[blk].len > BJ_MAX_ROWS) return;   // finished by the generic first-stage variants
   const int* hK = reinterpret_cast<const int*>(b.scratch_d + 7 * NV_MAX + OCMPS_MAX_BLK);
   const int keff = hK[OCMPS_MAX_BLK + blk];
   if (keff < 0) return;                                  // not handed over to this kernel
@@ -2317,7 +2326,7 @@ void profile_read(double* out) {
 }
 
 void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_launch, size_t smem_limit, bool need_global,
-                          bool long_rows, double rank_tol, int max_rows, int capV, int capC, cudaStream_t s) {
+                          bool long_rows, double rank_tol, int max_rows, int capV, int capC, cudaStream_t s, const SvdFork* fork) {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof_on) {
     if (g_prof_used == g_prof_events.size()) {
@@ -2355,34 +2364,45 @@ void launch_jacobi_blocks(const DecompArgs& a, const DecompBuffers& b, int nblk_
   // Hessian lose a fifth of their throughput (10.8 s vs 8.8 s) -- profiles/r02_results.md.
   static const bool gram_env = [] { const char* e = getenv("OCMPS_GRAM"); return e && e[0] == '1'; }();
   if (gram_env && (a.kind == DK_GATE_LEFT || a.kind == DK_GATE_RIGHT)) big_on |= 2;
+  // Two independent chains of kernels inside one decomposition: blocks that fit one SM (register-cached QR -> jacobi_rot_kernel) on
+  // `s`, blocks that need a cluster (qr_big_kernel -> jacobi_big_kernel) on the fork stream.  jacobi_big_kernel also takes the blocks
+  // the register-cached QR hands over with more than 64 rows of R, so it waits for that kernel as well.  (At chi = 256 the chains are
+  // 156 + 173 us and 180 + 431 us long: 0.61 ms per decomposition side by side instead of 0.94 ms one after the other.)
+  static const bool fork_env = [] { const char* e = getenv("OCMPS_SVD_FORK"); return !(e && e[0] == '0'); }();
+  const bool forked = fork_env && (big_on & 1) && fork && fork->stream;
+  cudaStream_t sb = forked ? fork->stream : s;
+  if (forked) { cudaEventRecord(fork->ev_fork, s); cudaStreamWaitEvent(sb, fork->ev_fork, 0); }
   jacobi_blocks_kernel<true, true><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol, big_on);
+  if (forked) cudaEventRecord(fork->ev_first, s);
   if (long_rows) jacobi_blocks_kernel<true, false><<<nblk_launch, JAC_THREADS, smem_limit, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol, big_on);
   if (need_global) jacobi_blocks_kernel<false, false><<<nblk_launch, JAC_THREADS, 0, s>>>(a, b, (int)(smem_limit / sizeof(cplx)), rank_tol, big_on);
-  // (after ALL first-stage variants: each of them publishes the hand-over flag of the blocks it owns)
-  if (big_on) {      // cluster QR of the blocks the register-cached kernel does not take (before the Jacobi kernels read the hand-over table)
+  // (after ALL first-stage variants of its stream: each of them publishes the hand-over flag of the blocks it owns)
+  if (big_on & 1) {      // cluster QR of the blocks the register-cached kernel does not take
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nblk_launch * BJ_C, 1, 1);
     cfg.blockDim = dim3(BJ_THREADS, 1, 1);
     cfg.dynamicSmemBytes = (size_t)(32 * BJ_MAX_ROWS + BJ_MAX_ROWS) * sizeof(cplx);
-    cfg.stream = s;
+    cfg.stream = sb;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = BJ_C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, qr_big_kernel, a, b, (int)(smem_limit / sizeof(cplx)), rank_tol);
   }
-  jacobi_rot_kernel<<<nblk_launch, JAC_THREADS, JAC_BLOCKED_ROWS * 16 * JAC_EPL * sizeof(cplx), s>>>(a, b);
-  if (big_on) {
+  jacobi_rot_kernel<<<nblk_launch, JAC_THREADS, JAC_BLOCKED_ROWS * 16 * JAC_EPL * sizeof(cplx), s>>>(a, b, (int)(smem_limit / sizeof(cplx)));
+  if (big_on & 1) {
+    if (forked) cudaStreamWaitEvent(sb, fork->ev_first, 0);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nblk_launch * BJ_C, 1, 1);
     cfg.blockDim = dim3(BJ_THREADS, 1, 1);
     cfg.dynamicSmemBytes = (size_t)BJ_MAX_ROWS * (BJ_TPP * BJ_MAX_EPL + 4) * sizeof(cplx);
-    cfg.stream = s;
+    cfg.stream = sb;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = BJ_C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, jacobi_big_kernel, a, b);
+    if (forked) { cudaEventRecord(fork->ev_join, sb); cudaStreamWaitEvent(s, fork->ev_join, 0); }
   }
 }
 

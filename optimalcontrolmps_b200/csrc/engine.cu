@@ -147,6 +147,9 @@ struct Workspace {
   DecompBuffers db2;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_trunc = nullptr, ev_setup = nullptr;
+  // Third stream: inside one decomposition the blocks that fit one SM (QR -> register-resident rotations) and the blocks that
+  // need a cluster (qr_big -> jacobi_big) are independent chains of kernels; the cluster chain runs on `side2` beside the other.
+  SvdFork fork;
   // overlaps
   cplx* E[2] = {nullptr, nullptr};
   cplx* T = nullptr;
@@ -268,6 +271,10 @@ int alloc_ws(ocmps_ctx* ctx, int L, int D, int cap, bool with_work, Workspace** 
   CK(cudaStreamCreateWithPriority(&w->side, cudaStreamNonBlocking, prio));
   CK(cudaEventCreateWithFlags(&w->ev_trunc, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&w->ev_setup, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithPriority(&w->fork.stream, cudaStreamNonBlocking, prio));
+  CK(cudaEventCreateWithFlags(&w->fork.ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&w->fork.ev_first, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&w->fork.ev_join, cudaEventDisableTiming));
   if (with_work) {
     int rc = alloc_mps(ctx, L, D, cap, &w->work);
     if (rc) return rc;
@@ -298,6 +305,10 @@ void free_ws(Workspace* w) {
   cudaFree(w->db2.dw); cudaFree(w->db2.vec_idx); cudaFree(w->db2.comp_idx); cudaFree(w->db2.vecq); cudaFree(w->db2.P);
   cudaFree(w->db2.pos); cudaFree(w->db2.ywork); cudaFree(w->db2.scratch_d); cudaFree(w->db2.descs);
   if (w->side) cudaStreamDestroy(w->side);
+  if (w->fork.stream) cudaStreamDestroy(w->fork.stream);
+  if (w->fork.ev_fork) cudaEventDestroy(w->fork.ev_fork);
+  if (w->fork.ev_first) cudaEventDestroy(w->fork.ev_first);
+  if (w->fork.ev_join) cudaEventDestroy(w->fork.ev_join);
   if (w->ev_trunc) cudaEventDestroy(w->ev_trunc);
   if (w->ev_setup) cudaEventDestroy(w->ev_setup);
   for (auto& kv : w->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -540,7 +551,7 @@ void run_decomp(Workspace* ws, const DecompArgs& a, const TruncParams& tp, int c
   rank_tol = std::min(rank_scale * 1e-8, std::max(1e-30, rank_tol));
   const bool long_rows = capV > 128;                   // rows of R longer than the register-cached path handles
   const int max_rows = std::min(capV, capC);           // rows of R of the largest possible block
-  launch_jacobi_blocks(a, db, nblk, smem, need_global, long_rows, rank_tol, max_rows, capV, capC, s);
+  launch_jacobi_blocks(a, db, nblk, smem, need_global, long_rows, rank_tol, max_rows, capV, capC, s, &ws->fork);
   g_trace.mark((a.kind == DK_GATE_LEFT || a.kind == DK_GATE_RIGHT) ? TR_SVD_GATE : TR_SVD_ORTH, s);
   launch_truncate(a, db, tp, s);
   g_trace.mark(TR_TRUNC, s);
