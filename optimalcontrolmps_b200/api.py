@@ -789,7 +789,7 @@ class OptimalControl:
         norms = np.zeros(N)
         divT = np.zeros(2 * N)
         fid = np.zeros(2 * N)
-        nch = self.hessian_chains or max(1, min(48, 12 * self.threadCount))   # measured (Nt=201, chi=100): 16 -> 25 s, 32 -> 16 s, 48 -> 14 s
+        nch = self.hessian_chains or max(1, min(64, 16 * self.threadCount))   # measured (Nt=201, chi=100): 12 -> much slower, 48 -> 8.84 s, 64 -> 8.43 s; the engine also bounds it by the free memory
         _lib.check(self.lib.ocmps_hessian_eval(self.timeStepper.h, self.psi_init.h, self.psi_target.h, _pd(u), N, self.psi_t.h,
                                                self.xi_t.h, self.xiHlist.h, _pi(rows), rows.size, nch, 1 if do_psi else 0,
                                                1 if do_xi else 0, _pd(divT), _pd(fid), _pd(ovl), _pd(norms)))
