@@ -274,3 +274,41 @@ def test_correlation_function_restatement_against_dense_state_vector():
                 assert abs(oo.correlation_function(psi, o1, i, o2, j) - dense(o1, i, o2, j)) < 1e-12
     rho = oo.correlation_matrix(psi, site_operator("Adag", D), site_operator("A", D))
     assert abs(np.trace(rho).real - Np) < 1e-12 and np.max(np.abs(rho - rho.conj().T)) < 1e-14
+
+
+def test_oracle_reproduces_the_start_of_the_cfg5_quench_golden():
+    """The committed golden of the cfg5 quench (tests/golden/make_golden_cfg5.py, 60 s of CPU) is checked here on its first 14 steps
+    (bond dimensions up to ~45, well under a second each): guards the golden against drift of the oracle."""
+    import os
+    import bench
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_cfg5_quench.npz"))
+    c = bench.CFG5
+    L, D = c["L"], c["d"] + 1
+    st = ob.BHStepper(L, D, c["J"], 5 * c["tstep"], ob.TruncArgs(cutoff=c["cutoff"], maxm=c["maxm"]))
+    psi0 = ob.product_state([1] * L, D)
+    psi = psi0.copy()
+    for k in range(14):
+        st.step(psi, 2.5, 2.5, True)
+        assert list(psi.bond_dims()) == z["dims"][k + 1].tolist()
+        assert abs(ob.overlap(psi0, psi) - complex(z["amp"][k + 1])) < 1e-12
+
+
+def test_oracle_reproduces_the_start_of_the_cfg4_sweep_golden():
+    """Same for the cfg4 sweep golden (tests/golden/make_golden_cfg4.py): the first 25 time points from the L=30 ground states."""
+    import os
+    import bench
+    from optimalcontrolmps_b200.states import ground_state
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_cfg4_sweep.npz"))
+    c = bench.CFG4
+    D = c["d"] + 1
+    conv = lambda h: ob.MPS(h.A, [np.asarray(x, dtype=np.int64) for x in h.q], 0, 2)
+    psi = conv(ground_state(c["L"], c["d"], c["Npart"], c["U_i"]))
+    target = conv(ground_state(c["L"], c["d"], c["Npart"], c["U_f"]))
+    st = ob.BHStepper(c["L"], D, c["J"], c["tstep"], ob.TruncArgs(cutoff=c["cutoff"], maxm=c["maxm"]))
+    u = z["u"]
+    assert list(psi.bond_dims()) == z["psi_dims"][0].tolist()
+    for k in range(24):
+        st.step(psi, u[k], u[k + 1], True)
+        assert list(psi.bond_dims()) == z["psi_dims"][k + 1].tolist()
+        f = abs(ob.overlap(target, psi)) ** 2
+        assert abs(f - z["fidelities"][k + 1]) <= 1e-12 * max(1.0, z["fidelities"][k + 1])
